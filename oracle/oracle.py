@@ -1,0 +1,309 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front-ends for the two CPU checkers.
+
+* ``Oracle``    -> oracle/_build/libnsfs_oracle.so, the plain-C restatement (nsfs_oracle.c)
+* ``Reference`` -> oracle/_ref/libnsfs_ref.so, the UNMODIFIED reference sources behind ref_harness.cpp
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  Both classes expose the same method names so a test can run either against the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libnsfs_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libnsfs_ref.so")
+
+ASTAR, DJIKSTRA, THETASTAR = 0, 1, 2
+MODE_F, MODE_G, MODE_FG = 0, 1, 2
+MODES = {"f": MODE_F, "g": MODE_G, "fg": MODE_FG}
+E_RANGE = -1
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """(Re)build both checkers with oracle/Makefile (the _ref target is a no-op without /root/reference)."""
+    if force or not os.path.exists(ORACLE_SO) or (
+        os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "nsfs_oracle.c"))
+    ):
+        subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    if os.path.isdir("/root/reference/src/global_planner") and (
+        force or not os.path.exists(REF_SO)
+        or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_harness.cpp"))
+    ):
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class _Stats(C.Structure):
+    _fields_ = [("pops", C.c_longlong), ("expansions", C.c_longlong), ("pushes", C.c_longlong),
+                ("heap_peak", C.c_longlong), ("los_checks", C.c_longlong)]
+
+
+class _Map(C.Structure):
+    _fields_ = [("H", C.c_int), ("W", C.c_int), ("infl", C.c_void_p), ("lo", C.c_void_p),
+                ("lo_thresh", C.c_int), ("cell", C.c_double), ("ox", C.c_double), ("oy", C.c_double)]
+
+
+class Oracle:
+    """Plain-C restatement.  ``infl``/``lo`` are int32 [H, W] arrays (kept alive by the object)."""
+
+    kind = "port"
+
+    def __init__(self, infl, lo, lo_thresh=10, cell=0.05, origin=(0.0, 0.0)):
+        build()
+        self.lib = C.CDLL(ORACLE_SO)
+        self.infl = np.ascontiguousarray(infl, dtype=np.int32)
+        self.lo = np.ascontiguousarray(lo, dtype=np.int32)
+        self.H, self.W = self.infl.shape
+        self.map = _Map(self.H, self.W, self.infl.ctypes.data, self.lo.ctypes.data, lo_thresh, cell,
+                        origin[0], origin[1])
+        L = self.lib
+        L.nso_dist_oct.restype = C.c_double
+        L.nso_dist_euc.restype = C.c_double
+
+    # -- planners ---------------------------------------------------------------------------------
+    def plan(self, algo, mode, start, goal, want_field=False, cap=None):
+        N = self.H * self.W
+        cap = cap or N + 1
+        path = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        gg = C.c_double(0)
+        st = _Stats()
+        g = np.zeros(N, np.float64) if want_field else None
+        par = np.zeros(N, np.int32) if want_field else None
+        vis = np.zeros(N, np.uint8) if want_field else None
+        rc = self.lib.nso_plan(C.byref(self.map), algo, MODES.get(mode, mode) if isinstance(mode, str) else mode,
+                               int(start[0]), int(start[1]), int(goal[0]), int(goal[1]),
+                               path.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(gg),
+                               g.ctypes.data_as(C.c_void_p) if want_field else None,
+                               par.ctypes.data_as(C.c_void_p) if want_field else None,
+                               vis.ctypes.data_as(C.c_void_p) if want_field else None, C.byref(st))
+        out = dict(status=rc, path=path[: n.value].copy(), g_goal=gg.value, settled=st.expansions,
+                   pops=st.pops, pushes=st.pushes, heap_peak=st.heap_peak, los_checks=st.los_checks)
+        if want_field:
+            out.update(g=g.reshape(self.H, self.W), parent=par.reshape(self.H, self.W),
+                       visited=vis.reshape(self.H, self.W))
+        return out
+
+    def field(self, start, mode="g"):
+        r = self.plan(DJIKSTRA, mode, start, (-7, -7), want_field=True, cap=4)
+        return r
+
+    def field_fixed_point(self, start):
+        g = np.zeros(self.H * self.W, np.float64)
+        rc = self.lib.nso_field_fixed_point(C.byref(self.map), int(start[0]), int(start[1]),
+                                            g.ctypes.data_as(C.c_void_p))
+        return rc, g.reshape(self.H, self.W)
+
+    def find_better_point(self, bad):
+        fi, fj = C.c_int(0), C.c_int(0)
+        st = _Stats()
+        rc = self.lib.nso_find_better_point(C.byref(self.map), int(bad[0]), int(bad[1]), C.byref(fi), C.byref(fj),
+                                            C.byref(st))
+        return dict(status=rc, cell=(fi.value, fj.value), settled=st.expansions, pops=st.pops)
+
+    # -- primitives -------------------------------------------------------------------------------
+    def test_pos(self, i, j):
+        return self.lib.nso_test_pos(C.byref(self.map), int(i), int(j))
+
+    def bresenham(self, s, t, closed=False):
+        n = max(abs(t[0] - s[0]), abs(t[1] - s[1])) + 1
+        out = np.zeros((n, 2), np.int32)
+        fn = self.lib.nso_bresenham_closed if closed else self.lib.nso_bresenham
+        m = fn(int(s[0]), int(s[1]), int(t[0]), int(t[1]), out.ctypes.data_as(C.c_void_p), n)
+        assert m == n
+        return out
+
+    def is_los(self, s, t):
+        return self.lib.nso_is_los(C.byref(self.map), int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def dist_oct(self, s, t):
+        return self.lib.nso_dist_oct(int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def dist_euc(self, s, t):
+        return self.lib.nso_dist_euc(int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def idx2pos(self, ij):
+        ij = np.asarray(ij, np.float64).reshape(-1, 2)
+        # grid_planner_core.cpp:416-421, evaluated in double exactly as written there
+        return np.stack([ij[:, 0] * self.map.cell + self.map.ox, ij[:, 1] * self.map.cell + self.map.oy], 1)
+
+    def _xy_call(self, fn, xy, with_map=True):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        out = np.zeros((max(len(xy), 2) + 2, 2), np.float64)
+        args = [xy.ctypes.data_as(C.c_void_p), len(xy), out.ctypes.data_as(C.c_void_p), len(out)]
+        n = fn(C.byref(self.map), *args) if with_map else fn(*args)
+        return out[:n].copy() if n >= 0 else n
+
+    def sparsify(self, xy):
+        return self._xy_call(self.lib.nso_sparsify, xy, with_map=False)
+
+    def any_angle(self, xy):
+        return self._xy_call(self.lib.nso_any_angle, xy)
+
+    def post_process(self, xy):
+        return self._xy_call(self.lib.nso_post_process, xy)
+
+    def generate_path(self, algo, mode, start, goal):
+        """generatePath == plan + post_process_path, world coordinates (grid_planner_core.cpp:603-608)."""
+        r = self.plan(algo, mode, start, goal)
+        if r["status"] != 0:
+            return r
+        r["final_xy"] = self.post_process(self.idx2pos(r["path"]))
+        return r
+
+    def heap_trace(self, mode, ops):
+        ops = np.ascontiguousarray(ops, np.int32).reshape(-1, 4)
+        out = np.zeros(len(ops), np.int32)
+        n = self.lib.nso_heap_trace(MODES[mode], len(ops), ops.ctypes.data_as(C.c_void_p),
+                                    out.ctypes.data_as(C.c_void_p))
+        return out[:n].copy()
+
+
+class Reference:
+    """The reference's own planners (compiled from /root/reference, unmodified)."""
+
+    kind = "reference"
+
+    def __init__(self, infl, lo, lo_thresh=10, cell=0.05, origin=(0.0, 0.0)):
+        if not have_reference():
+            build()
+        if not have_reference():
+            raise FileNotFoundError(REF_SO)
+        self.lib = L = C.CDLL(REF_SO)
+        self.infl = np.ascontiguousarray(infl, dtype=np.int32)
+        self.lo = np.ascontiguousarray(lo, dtype=np.int32)
+        self.H, self.W = self.infl.shape
+        self.cell, self.origin = cell, origin
+        L.nsref_create.restype = C.c_void_p
+        L.nsref_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        L.nsref_destroy.argtypes = [C.c_void_p]
+        L.nsref_dist_oct.restype = C.c_double
+        L.nsref_dist_euc.restype = C.c_double
+        self.ctx = C.c_void_p(L.nsref_create(self.H, self.W, cell, origin[0], origin[1], self.infl.ctypes.data,
+                                             self.lo.ctypes.data, lo_thresh))
+
+    def __del__(self):
+        try:
+            self.lib.nsref_destroy(self.ctx)
+        except Exception:
+            pass
+
+    def plan(self, algo, mode, start, goal, post=False, cap=None):
+        N = self.H * self.W
+        cap = cap or N + 1
+        xy = np.zeros((cap, 2), np.float64)
+        ij = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        gg = C.c_double(0)
+        settled = C.c_longlong(0)
+        sec = C.c_double(0)
+        rc = self.lib.nsref_plan(self.ctx, algo, MODES.get(mode, mode) if isinstance(mode, str) else mode,
+                                 int(start[0]), int(start[1]), int(goal[0]), int(goal[1]), int(post),
+                                 xy.ctypes.data_as(C.c_void_p), ij.ctypes.data_as(C.c_void_p), cap,
+                                 C.byref(n), C.byref(gg), C.byref(settled), C.byref(sec))
+        return dict(status=rc, path=ij[: n.value].copy(), xy=xy[: n.value].copy(), g_goal=gg.value,
+                    settled=settled.value, seconds=sec.value)
+
+    def generate_path(self, algo, mode, start, goal):
+        raw = self.plan(algo, mode, start, goal, post=False)
+        fin = self.plan(algo, mode, start, goal, post=True)
+        raw["final_xy"] = fin["xy"]
+        raw["seconds"] = fin["seconds"]
+        return raw
+
+    def field(self, start, mode="g"):
+        N = self.H * self.W
+        g = np.zeros(N, np.float64)
+        par = np.zeros(N, np.int32)
+        vis = np.zeros(N, np.uint8)
+        settled = C.c_longlong(0)
+        sec = C.c_double(0)
+        rc = self.lib.nsref_field(self.ctx, MODES[mode], int(start[0]), int(start[1]), g.ctypes.data_as(C.c_void_p),
+                                  par.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p),
+                                  C.byref(settled), C.byref(sec))
+        return dict(status=rc, g=g.reshape(self.H, self.W), parent=par.reshape(self.H, self.W),
+                    visited=vis.reshape(self.H, self.W), settled=settled.value, seconds=sec.value)
+
+    def find_better_point(self, bad):
+        fi, fj = C.c_int(0), C.c_int(0)
+        x, y = C.c_double(0), C.c_double(0)
+        settled = C.c_longlong(0)
+        sec = C.c_double(0)
+        rc = self.lib.nsref_find_better_point(self.ctx, int(bad[0]), int(bad[1]), C.byref(fi), C.byref(fj),
+                                              C.byref(x), C.byref(y), C.byref(settled), C.byref(sec))
+        return dict(status=rc, cell=(fi.value, fj.value), xy=(x.value, y.value), settled=settled.value,
+                    seconds=sec.value)
+
+    def test_pos(self, i, j):
+        return self.lib.nsref_test_pos(self.ctx, int(i), int(j))
+
+    def bresenham(self, s, t, closed=False):
+        n = max(abs(t[0] - s[0]), abs(t[1] - s[1])) + 1
+        out = np.zeros((n, 2), np.int32)
+        m = self.lib.nsref_bresenham(int(s[0]), int(s[1]), int(t[0]), int(t[1]), out.ctypes.data_as(C.c_void_p), n)
+        assert m == n
+        return out
+
+    def is_los(self, s, t):
+        return self.lib.nsref_is_los(self.ctx, int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def dist_oct(self, s, t):
+        return self.lib.nsref_dist_oct(int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def dist_euc(self, s, t):
+        return self.lib.nsref_dist_euc(int(s[0]), int(s[1]), int(t[0]), int(t[1]))
+
+    def idx2pos(self, ij):
+        ij = np.asarray(ij, np.int64).reshape(-1, 2)
+        out = np.zeros((len(ij), 2), np.float64)
+        x, y = C.c_double(0), C.c_double(0)
+        for t, (i, j) in enumerate(ij):
+            self.lib.nsref_idx2pos(self.ctx, int(i), int(j), C.byref(x), C.byref(y))
+            out[t] = (x.value, y.value)
+        return out
+
+    def _xy_call(self, fn, xy, *pre):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        out = np.zeros((max(len(xy), 2) + 2, 2), np.float64)
+        n = fn(self.ctx, *pre, xy.ctypes.data_as(C.c_void_p), len(xy), out.ctypes.data_as(C.c_void_p), len(out))
+        return out[:n].copy() if n >= 0 else n
+
+    def sparsify(self, xy):
+        return self._xy_call(self.lib.nsref_sparsify, xy)
+
+    def any_angle(self, xy):
+        return self._xy_call(self.lib.nsref_any_angle, xy)
+
+    def post_process(self, xy, algo=ASTAR):
+        return self._xy_call(self.lib.nsref_post_process, xy, algo)
+
+    def heap_trace(self, mode, ops):
+        ops = np.ascontiguousarray(ops, np.int32).reshape(-1, 4)
+        out = np.zeros(len(ops), np.int32)
+        n = self.lib.nsref_heap_trace(MODES[mode], len(ops), ops.ctypes.data_as(C.c_void_p),
+                                      out.ctypes.data_as(C.c_void_p))
+        return out[:n].copy()
+
+    def plan_batch(self, algo, mode, sg4, nthreads=1):
+        sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)
+        nq = len(sg4)
+        g = np.zeros(nq, np.float64)
+        plen = np.zeros(nq, np.int32)
+        settled = np.zeros(nq, np.int64)
+        sec = C.c_double(0)
+        rc = self.lib.nsref_plan_batch(self.ctx, algo, MODES[mode], nq, sg4.ctypes.data_as(C.c_void_p), int(nthreads),
+                                       g.ctypes.data_as(C.c_void_p), plen.ctypes.data_as(C.c_void_p),
+                                       settled.ctypes.data_as(C.c_void_p), C.byref(sec))
+        return dict(status=rc, g_goal=g, path_len=plen, settled=settled, seconds=sec.value)
