@@ -1,0 +1,146 @@
+/* nsfs.h — C-ABI of the B200 grid planner (libnsfs_gpu.so).
+ *
+ * Drop-in boundary for the grid-search hot path of mukundbala/Nav-Stack-From-Scratch's global_planner.
+ * Every entry point names the reference interface it stands in for (paths relative to the reference
+ * root; "core.cpp" = src/global_planner/src/algo/grid_planner_core.cpp).  Plain pointers and sizes only:
+ * no STL, no exceptions, no torch types cross this boundary.  The C++17 children in
+ * nav-stack-from-scratch_b200/host/ (GpuAstar / GpuDjikstra / GpuThetaStar : GridPlannerCore) are the only
+ * intended callers on the reference side; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - Cells are (i, j) with flat key k = i*W + j, i <-> x, j <-> y (reference occupancy_grid.cpp:215-218).
+ *   - A cell is free iff infl[k] <= 0 && lo[k] <= lo_thresh (testPos, core.cpp:434-455).
+ *   - Paths are int32 (i, j) pairs ordered goal -> start, as plan() returns them (astar.cpp:68-85,138-147);
+ *     "no path" is the single start cell (astar.cpp:129-135).  World coordinates are formed by the C++
+ *     adapter in double (idx2pos, core.cpp:416-421).
+ *   - Return value: NSFS_OK or a negative NSFS_E_* code.  NSFS_E_RANGE is the reference's
+ *     std::out_of_range (vector::at in testPos); the adapter re-throws it.
+ *   - One CUDA stream per handle; calls on one handle are not re-entrant (the reference planners are
+ *     single-threaded objects too).  Host pointers are borrowed for the duration of the call.
+ *   - There is no CPU fallback: every compute call fails with NSFS_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef NSFS_H
+#define NSFS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSFS_OK          0
+#define NSFS_E_RANGE    -1   /* reference would throw std::out_of_range */
+#define NSFS_E_CUDA     -2   /* CUDA runtime error; nsfs_last_cuda_error() has the text */
+#define NSFS_E_TRUNC    -3   /* caller's output buffer too small (n_path still reports the full length) */
+#define NSFS_E_ARG      -4   /* bad argument (start outside the grid, unknown algo, NULL handle, ...) */
+#define NSFS_E_NOMEM    -5
+#define NSFS_E_HEAP     -6   /* open list outgrew its device capacity even after the internal retry */
+#define NSFS_E_NOMAP    -7   /* no map has been set on this handle */
+#define NSFS_E_NOFIELD  -8   /* nsfs_field_path() before nsfs_field() */
+
+/* planner_name (global_planner.cpp:104-125) */
+#define NSFS_ASTAR           0   /* Astar::plan, astar.cpp:27-148: exact open-list order emulation */
+#define NSFS_DJIKSTRA        1   /* Djikstra::plan, djikstra.cpp:27-145: exact open-list order emulation */
+#define NSFS_THETASTAR       2   /* no reference implementation (thetastar.cpp is empty): designed here */
+#define NSFS_DJIKSTRA_FIELD  3   /* Djikstra::plan by bulk relaxation of the cost-to-go field + predecessor walk:
+                                    same reachability and cost, possibly another equal-cost path */
+
+/* cost_mode (core.cpp:243-283): OpenList comparator */
+#define NSFS_MODE_F   0
+#define NSFS_MODE_G   1
+#define NSFS_MODE_FG  2
+
+typedef struct nsfs_planner nsfs_t;
+
+typedef struct nsfs_stats {
+    long long pops;          /* OpenList::popNode calls               (search calls) */
+    long long expansions;    /* non-stale pops = settled cells        (search calls); reached cells (field) */
+    long long pushes;        /* OpenList::pushNode calls */
+    long long heap_peak;     /* largest open-list length */
+    long long los_checks;    /* isLos evaluations (ThetaStar) */
+    long long rounds;        /* global relaxation rounds (field) */
+    long long tile_visits;   /* tile relaxations (field) */
+    long long launches;      /* kernels launched by this call */
+    float     gpu_ms;        /* device time of the call's kernels (CUDA events on the handle's stream) */
+} nsfs_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------
+ * replaces: GridPlannerCore(cost_mode, map) / prepPlanner (core.cpp:353-383,570-600), which size the
+ * per-cell Node store from map_size_.  device = CUDA ordinal. */
+int  nsfs_create(nsfs_t** out, int H, int W, int device);
+void nsfs_destroy(nsfs_t* h);
+
+/* ---- map -----------------------------------------------------------------------------------------
+ * replaces: the MapData& argument every reference call takes (map_data.h:8-20).  The reference re-reads
+ * the caller's vectors on every call; here the caller hands them over whenever they changed
+ * (global_planner.cpp:65-73 replaces them per ROS callback).  Packs to 1 bit/cell free + 1 bit/cell
+ * inflated planes and the per-cell edge masks on the device. */
+int nsfs_set_map(nsfs_t* h, const int32_t* infl, const int32_t* lo, int lo_thresh);          /* host pointers   */
+int nsfs_set_map_device(nsfs_t* h, const int32_t* d_infl, const int32_t* d_lo, int lo_thresh); /* device pointers */
+/* Packed planes for shipping a map between GPUs (N/4 bytes instead of 8N): words = (H*W + 31) / 32 each. */
+int nsfs_map_words(const nsfs_t* h);
+int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_t** d_inflated);
+int nsfs_set_packed_map_device(nsfs_t* h, const uint32_t* d_free, const uint32_t* d_inflated);
+/* testPos(Index) for a batch of cells (core.cpp:434-455): out = 1 free, 0 not free / row out of range, -1 would throw */
+int nsfs_test_pos_batch(nsfs_t* h, int n, const int32_t* ij, int8_t* out);
+
+/* ---- single query --------------------------------------------------------------------------------
+ * replaces: GridPlannerCore::plan(Index, Index, MapData&) of the selected child.
+ * path_ij: cap (i,j) pairs; n_path = number of path cells; g_goal = nodes[goal].g after the search
+ * (1e5 when unreachable).  Any of path_ij / n_path / g_goal / st may be NULL. */
+int nsfs_plan(nsfs_t* h, int algo, int cost_mode, int si, int sj, int gi, int gj,
+              int32_t* path_ij, int cap, int* n_path, double* g_goal, nsfs_stats* st);
+
+/* ---- batched queries -----------------------------------------------------------------------------
+ * nq independent plan() calls on the current map; sg4[4q..] = {si, sj, gi, gj}.
+ * Per query: status (NSFS_OK / NSFS_E_RANGE / NSFS_E_HEAP), g_goal, path_len (cells), settled (expansions).
+ * paths_ij (optional) receives min(path_len, path_cap) cells per query at stride path_cap. */
+int nsfs_plan_batch(nsfs_t* h, int algo, int cost_mode, int nq, const int32_t* sg4,
+                    int32_t* status, double* g_goal, int32_t* path_len, long long* settled,
+                    int32_t* paths_ij, int path_cap, nsfs_stats* st);
+/* Same, with every array already resident on the handle's device (no copies inside the call). */
+int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int32_t* d_sg4,
+                           int32_t* d_status, double* d_g_goal, int32_t* d_path_len, long long* d_settled,
+                           int32_t* d_paths_ij, int path_cap, nsfs_stats* st);
+
+/* ---- cost-to-go field ----------------------------------------------------------------------------
+ * replaces: Djikstra::plan with an unreachable goal, i.e. nodes[k].g for every k (djikstra.cpp:27-145).
+ * g: fp32 [H*W], 1e5 = unreached.  pred: direction code d in 0..7 of the incoming edge (parent key =
+ * k - OFF[d], OFF = {+W, +W+1, +1, -W+1, -W, -W-1, -1, +W-1}, NB_LUT order grid_planner_core.h:197),
+ * 255 = none (unreached or the source).  Either host pointer may be NULL. */
+int nsfs_field(nsfs_t* h, int si, int sj, float* g, uint8_t* pred, nsfs_stats* st);
+/* Same, result left on the device; the pointers stay valid until the next field call on this handle. */
+int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_t** d_pred, nsfs_stats* st);
+/* Walk the predecessor field of the last nsfs_field* call from (gi, gj) back to its source.
+ * cost = (#cardinal-cost steps) + (#diagonal-cost steps) * sqrt(2) in double. */
+int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n_path, double* cost);
+
+/* ---- fallback ------------------------------------------------------------------------------------
+ * replaces: Djikstra::find_better_point(Index, MapData&) (djikstra.cpp:165-273) on a planner prepared
+ * with cost mode "g" (global_planner.cpp:127-128).  (fi, fj) = first popped free cell, or the input cell
+ * when none is found (djikstra.cpp:272). */
+int nsfs_find_better_point(nsfs_t* h, int bi, int bj, int* fi, int* fj, nsfs_stats* st);
+int nsfs_find_better_point_batch(nsfs_t* h, int n, const int32_t* bad_ij, int32_t* out_ij, int32_t* status,
+                                 nsfs_stats* st);
+
+/* ---- line of sight and post-processing -----------------------------------------------------------
+ * replaces: GridPlannerCore::isLos(Index, Index, MapData&) (core.cpp:481-496) over bresenham_los
+ * (bot_utils.cpp:137-192).  seg4[4s..] = {si, sj, ti, tj}; out = 1 LOS, 0 blocked, -1 would throw. */
+int nsfs_los_batch(nsfs_t* h, int n, const int32_t* seg4, int8_t* out);
+/* replaces: the isLos loop of makeAnyAnglePath (core.cpp:537-558) over turning points already converted
+ * with pos2idx.  keep[t] = 1 if point t survives (first and last always do). */
+int nsfs_any_angle(nsfs_t* h, int n, const int32_t* pts_ij, uint8_t* keep);
+
+/* ---- service -------------------------------------------------------------------------------------*/
+int         nsfs_sync(nsfs_t* h);
+long long   nsfs_kernel_launches(const nsfs_t* h);   /* kernels launched through this handle so far */
+void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the handle */
+int         nsfs_set_option(nsfs_t* h, const char* key, long long value);
+const char* nsfs_strerror(int code);
+const char* nsfs_last_cuda_error(const nsfs_t* h);
+const char* nsfs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSFS_H */

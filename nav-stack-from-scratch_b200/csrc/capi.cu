@@ -1,0 +1,468 @@
+// extern "C" surface of libnsfs_gpu.so (include/nsfs.h): argument checks, staging copies, launches, results.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "nsfs_internal.cuh"
+
+namespace nsfs {
+
+int set_cuda_error(nsfs_planner* h, cudaError_t e, const char* where) {
+    if (h) snprintf(h->cuda_error, sizeof(h->cuda_error), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
+    cudaGetLastError();   // clear the sticky-less error state
+    return NSFS_E_CUDA;
+}
+
+static int ensure_scratch(nsfs_planner* h, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes <= h->scratch_bytes) return NSFS_OK;
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    h->d_scratch = nullptr; h->scratch_bytes = 0;
+    NSFS_CUDA_TRY(h, cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_bytes = bytes;
+    return NSFS_OK;
+}
+
+struct Timer {
+    nsfs_planner* h;
+    explicit Timer(nsfs_planner* h_) : h(h_) { cudaEventRecord(h->ev0, h->stream); }
+    float stop_sync() {
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        return ms;
+    }
+};
+
+static int enter(nsfs_planner* h, bool need_map) {
+    if (!h) return NSFS_E_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return set_cuda_error(h, cudaGetLastError(), "cudaSetDevice");
+    if (need_map && !h->have_map) return NSFS_E_NOMAP;
+    return NSFS_OK;
+}
+
+static int finish_map(nsfs_planner* h) {
+    int rc = launch_build_masks(h);
+    if (rc != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_map = true;
+    h->field.valid = false;
+    return NSFS_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace nsfs
+
+using namespace nsfs;
+
+extern "C" {
+
+int nsfs_create(nsfs_t** out, int H, int W, int device) {
+    if (!out || H <= 0 || W <= 0) return NSFS_E_ARG;
+    const long long N = (long long)H * W;
+    if (N >= (1ll << 29)) return NSFS_E_ARG;            // open-list entries carry a 29-bit key
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return NSFS_E_CUDA;                              // no CPU fallback exists
+    }
+    nsfs_planner* h = new (std::nothrow) nsfs_planner();
+    if (!h) return NSFS_E_NOMEM;
+    h->H = H; h->W = W; h->N = N; h->device = device;
+    int rc = NSFS_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = set_cuda_error(h, cudaGetLastError(), "cudaSetDevice"); break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_cuda_error(h, cudaGetLastError(), "cudaGetDeviceProperties"); break; }
+        h->sm_count = prop.multiProcessorCount;
+        const size_t words = (size_t)((N + 31) / 32) + 8;
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+            (e = cudaMalloc(&h->d_free, words * 4)) != cudaSuccess || (e = cudaMalloc(&h->d_inflated, words * 4)) != cudaSuccess ||
+            (e = cudaMalloc(&h->d_out_mask, (size_t)N * 2)) != cudaSuccess || (e = cudaMalloc(&h->d_in_mask, (size_t)N * 2)) != cudaSuccess ||
+            (e = cudaMemsetAsync(h->d_free, 0, words * 4, h->stream)) != cudaSuccess ||
+            (e = cudaMemsetAsync(h->d_inflated, 0, words * 4, h->stream)) != cudaSuccess) {
+            rc = set_cuda_error(h, e, "nsfs_create allocations");
+            break;
+        }
+        rc = ensure_scratch(h, 1 << 16);
+    } while (0);
+    if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
+    *out = h;
+    return NSFS_OK;
+}
+
+void nsfs_destroy(nsfs_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    field_free(h);
+    search_free(h);
+    cudaFree(h->d_infl); cudaFree(h->d_lo); cudaFree(h->d_free); cudaFree(h->d_inflated);
+    cudaFree(h->d_out_mask); cudaFree(h->d_in_mask); cudaFree(h->d_scratch);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+int nsfs_set_map(nsfs_t* h, const int32_t* infl, const int32_t* lo, int lo_thresh) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!infl || !lo) return NSFS_E_ARG;
+    const size_t bytes = (size_t)h->N * sizeof(int32_t);
+    if (!h->d_infl) {
+        NSFS_CUDA_TRY(h, cudaMalloc(&h->d_infl, bytes + 16));
+        NSFS_CUDA_TRY(h, cudaMalloc(&h->d_lo, bytes + 16));
+    }
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_infl, infl, bytes, cudaMemcpyHostToDevice, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lo, lo, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->lo_thresh = lo_thresh;
+    rc = launch_pack_map(h, h->d_infl, h->d_lo);
+    if (rc != NSFS_OK) return rc;
+    return finish_map(h);
+}
+
+int nsfs_set_map_device(nsfs_t* h, const int32_t* d_infl, const int32_t* d_lo, int lo_thresh) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!d_infl || !d_lo || ((uintptr_t)d_infl & 15) || ((uintptr_t)d_lo & 15)) return NSFS_E_ARG;   // 128-bit loads
+    h->lo_thresh = lo_thresh;
+    rc = launch_pack_map(h, d_infl, d_lo);
+    if (rc != NSFS_OK) return rc;
+    return finish_map(h);
+}
+
+int nsfs_map_words(const nsfs_t* h) { return h ? (int)((h->N + 31) / 32) : 0; }
+
+int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_t** d_inflated) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (d_free) *d_free = h->d_free;
+    if (d_inflated) *d_inflated = h->d_inflated;
+    return NSFS_OK;
+}
+
+int nsfs_set_packed_map_device(nsfs_t* h, const uint32_t* d_free, const uint32_t* d_inflated) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!d_free || !d_inflated) return NSFS_E_ARG;
+    const size_t bytes = (size_t)((h->N + 31) / 32) * 4;
+    if (d_free != h->d_free) NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_free, d_free, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (d_inflated != h->d_inflated) NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_inflated, d_inflated, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return finish_map(h);
+}
+
+int nsfs_test_pos_batch(nsfs_t* h, int n, const int32_t* ij, int8_t* out) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (n < 0 || (n && (!ij || !out))) return NSFS_E_ARG;
+    if (!n) return NSFS_OK;
+    const size_t in_b = align_up((size_t)n * 8, 256);
+    if ((rc = ensure_scratch(h, in_b + n)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d, ij, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_test_pos(h, n, (const int32_t*)d, (int8_t*)(d + in_b))) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(out, d + in_b, n, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+// ---- searches ------------------------------------------------------------------------------------------
+static void fill_stats(nsfs_stats* st, const long long* s5, long long launches, float ms) {
+    if (!st) return;
+    memset(st, 0, sizeof(*st));
+    st->pops = s5[0]; st->expansions = s5[1]; st->pushes = s5[2]; st->heap_peak = s5[3]; st->los_checks = s5[4];
+    st->launches = launches; st->gpu_ms = ms;
+}
+
+// Runs nq queries given as host arrays; kind 0 = plan, 1 = find_better_point.  Retries open-list overflows once
+// with the provable upper bound on the open-list length (every directed edge is relaxed at most once => 8N+1).
+static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* q_host,
+                           int32_t* status, double* g_goal, int32_t* path_len, long long* settled,
+                           int32_t* paths, int path_cap, nsfs_stats* st) {
+    const int qw = kind == 1 ? 2 : 4;
+    const long long launches0 = h->launches;
+    const size_t o_q = 0;
+    const size_t o_status = align_up(o_q + (size_t)nq * qw * 4, 256);
+    const size_t o_g = align_up(o_status + (size_t)nq * 4, 256);
+    const size_t o_len = align_up(o_g + (size_t)nq * 8, 256);
+    const size_t o_set = align_up(o_len + (size_t)nq * 4, 256);
+    const size_t o_s5 = align_up(o_set + (size_t)nq * 8, 256);
+    const size_t o_paths = align_up(o_s5 + 5 * 8, 256);
+    const size_t path_elems = kind == 1 ? (size_t)nq * 2 : (paths ? (size_t)nq * (size_t)path_cap * 2 : 0);
+    int rc = ensure_scratch(h, o_paths + path_elems * 4 + 256);
+    if (rc != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d + o_q, q_host, (size_t)nq * qw * 4, cudaMemcpyHostToDevice, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(d + o_s5, 0, 5 * 8, h->stream));
+    if ((rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    Timer tm(h);
+    rc = launch_search(h, kind, algo, mode, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (double*)(d + o_g),
+                       (int32_t*)(d + o_len), (long long*)(d + o_set), path_elems ? (int32_t*)(d + o_paths) : nullptr, path_cap,
+                       (long long*)(d + o_s5));
+    if (rc != NSFS_OK) return rc;
+    const float ms = tm.stop_sync();
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    std::vector<int32_t> stat_h(nq);
+    long long s5[5];
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(stat_h.data(), d + o_status, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(s5, d + o_s5, sizeof(s5), cudaMemcpyDeviceToHost, h->stream));
+    if (g_goal) NSFS_CUDA_TRY(h, cudaMemcpyAsync(g_goal, d + o_g, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (path_len) NSFS_CUDA_TRY(h, cudaMemcpyAsync(path_len, d + o_len, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (settled) NSFS_CUDA_TRY(h, cudaMemcpyAsync(settled, d + o_set, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (paths && path_elems) NSFS_CUDA_TRY(h, cudaMemcpyAsync(paths, d + o_paths, path_elems * 4, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (status) memcpy(status, stat_h.data(), (size_t)nq * 4);
+    fill_stats(st, s5, h->launches - launches0, ms);
+
+    // ---- open-list overflow: redo those queries one at a time with the worst-case capacity ----------------
+    const long long worst = 8 * h->N + 16;
+    for (int q = 0; q < nq; ++q) {
+        if (stat_h[q] != NSFS_E_HEAP || h->search.heap_cap >= worst) continue;
+        const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots;
+        h->opt_heap_cap = worst; h->opt_max_slots = 1;
+        search_free(h);
+        int32_t s1 = 0; double g1 = 0; int32_t l1 = 0; long long e1 = 0;
+        std::vector<int32_t> p1(paths ? (size_t)path_cap * 2 : (kind == 1 ? 2 : 0));
+        rc = run_search_host(h, kind, algo, mode, 1, q_host + (size_t)q * qw, &s1, &g1, &l1, &e1, p1.empty() ? nullptr : p1.data(),
+                             path_cap, nullptr);
+        h->opt_heap_cap = keep_cap; h->opt_max_slots = keep_slots;
+        search_free(h);
+        if (rc != NSFS_OK) return rc;
+        if (status) status[q] = s1;
+        if (g_goal) g_goal[q] = g1;
+        if (path_len) path_len[q] = l1;
+        if (settled) settled[q] = e1;
+        if (paths && !p1.empty()) memcpy(paths + (size_t)q * (kind == 1 ? 2 : (size_t)path_cap * 2), p1.data(), p1.size() * 4);
+    }
+    return NSFS_OK;
+}
+
+int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_t** d_pred, nsfs_stats* st);
+int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n_path, double* cost);
+
+int nsfs_plan(nsfs_t* h, int algo, int cost_mode, int si, int sj, int gi, int gj, int32_t* path_ij, int cap, int* n_path,
+              double* g_goal, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (si < 0 || si >= h->H || sj < 0 || sj >= h->W || cap < 0) return NSFS_E_ARG;
+    if (algo == NSFS_DJIKSTRA_FIELD) {
+        nsfs_stats fs;
+        rc = nsfs_field_device(h, si, sj, nullptr, nullptr, &fs);
+        if (rc != NSFS_OK) return rc;
+        int n = 0; double cost = 0;
+        rc = nsfs_field_path(h, gi, gj, path_ij, path_ij ? cap : 0, &n, &cost);
+        if (n_path) *n_path = n;
+        if (g_goal) *g_goal = cost;
+        if (st) { *st = fs; st->launches += 1; }
+        if (rc == NSFS_E_TRUNC && !path_ij) rc = NSFS_OK;
+        return rc;
+    }
+    if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
+    const int32_t q[4] = {si, sj, gi, gj};
+    int32_t status = 0, len = 0;
+    long long cap_ll = cap;
+    if (cap_ll > h->N + 1) cap_ll = h->N + 1;
+    rc = run_search_host(h, 0, algo, cost_mode, 1, q, &status, g_goal, &len, nullptr, path_ij, path_ij ? (int)cap_ll : 0, st);
+    if (rc != NSFS_OK) return rc;
+    if (n_path) *n_path = len;
+    if (status != NSFS_OK) return status;
+    if (path_ij && len > cap) return NSFS_E_TRUNC;
+    return NSFS_OK;
+}
+
+int nsfs_plan_batch(nsfs_t* h, int algo, int cost_mode, int nq, const int32_t* sg4, int32_t* status, double* g_goal,
+                    int32_t* path_len, long long* settled, int32_t* paths_ij, int path_cap, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (nq < 0 || (nq && !sg4) || path_cap < 0) return NSFS_E_ARG;
+    if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
+    if (!nq) return NSFS_OK;
+    return run_search_host(h, 0, algo, cost_mode, nq, sg4, status, g_goal, path_len, settled, paths_ij, path_cap, st);
+}
+
+int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int32_t* d_sg4, int32_t* d_status, double* d_g_goal,
+                           int32_t* d_path_len, long long* d_settled, int32_t* d_paths_ij, int path_cap, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (nq < 0 || (nq && !d_sg4) || path_cap < 0) return NSFS_E_ARG;
+    if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
+    if (!nq) return NSFS_OK;
+    const long long launches0 = h->launches;
+    if ((rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    long long* d_s5 = nullptr;
+    if (st) {
+        if ((rc = ensure_scratch(h, 256)) != NSFS_OK) return rc;
+        d_s5 = (long long*)h->d_scratch;
+        NSFS_CUDA_TRY(h, cudaMemsetAsync(d_s5, 0, 5 * 8, h->stream));
+    }
+    Timer tm(h);
+    rc = launch_search(h, 0, algo, cost_mode, nq, d_sg4, d_status, d_g_goal, d_path_len, d_settled, d_paths_ij, path_cap, d_s5);
+    if (rc != NSFS_OK) return rc;
+    if (st) {
+        const float ms = tm.stop_sync();
+        long long s5[5];
+        NSFS_CUDA_TRY(h, cudaMemcpy(s5, d_s5, sizeof(s5), cudaMemcpyDeviceToHost));
+        fill_stats(st, s5, h->launches - launches0, ms);
+    }
+    return NSFS_OK;
+}
+
+int nsfs_find_better_point_batch(nsfs_t* h, int n, const int32_t* bad_ij, int32_t* out_ij, int32_t* status, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (n < 0 || (n && (!bad_ij || !out_ij))) return NSFS_E_ARG;
+    if (!n) return NSFS_OK;
+    for (int t = 0; t < n; ++t)
+        if (bad_ij[2 * t] < 0 || bad_ij[2 * t] >= h->H || bad_ij[2 * t + 1] < 0 || bad_ij[2 * t + 1] >= h->W) return NSFS_E_ARG;
+    return run_search_host(h, 1, NSFS_DJIKSTRA, NSFS_MODE_G, n, bad_ij, status, nullptr, nullptr, nullptr, out_ij, 1, st);
+}
+
+int nsfs_find_better_point(nsfs_t* h, int bi, int bj, int* fi, int* fj, nsfs_stats* st) {
+    const int32_t q[2] = {bi, bj};
+    int32_t out[2] = {bi, bj}, status = 0;
+    int rc = nsfs_find_better_point_batch(h, 1, q, out, &status, st);
+    if (rc != NSFS_OK) return rc;
+    if (fi) *fi = out[0];
+    if (fj) *fj = out[1];
+    return status;
+}
+
+// ---- field ------------------------------------------------------------------------------------------------
+int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_t** d_pred, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (si < 0 || si >= h->H || sj < 0 || sj >= h->W) return NSFS_E_ARG;
+    const long long launches0 = h->launches;
+    Timer tm(h);
+    rc = launch_field(h, si, sj, st);
+    if (rc != NSFS_OK) return rc;
+    const float ms = tm.stop_sync();
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    int counts[8];
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(counts, h->field.counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5]; st->pops = counts[6];
+        st->launches = h->launches - launches0; st->gpu_ms = ms;
+    }
+    if (d_g) *d_g = h->field.g;
+    if (d_pred) *d_pred = h->field.pred;
+    if (counts[4]) return NSFS_E_RANGE;     // a reached cell's expansion throws in the reference
+    h->field.valid = true;
+    return NSFS_OK;
+}
+
+int nsfs_field(nsfs_t* h, int si, int sj, float* g, uint8_t* pred, nsfs_stats* st) {
+    int rc = nsfs_field_device(h, si, sj, nullptr, nullptr, st);
+    if (rc != NSFS_OK) return rc;
+    if (g) NSFS_CUDA_TRY(h, cudaMemcpyAsync(g, h->field.g, (size_t)h->N * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (pred) NSFS_CUDA_TRY(h, cudaMemcpyAsync(pred, h->field.pred, (size_t)h->N, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n_path, double* cost) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.valid) return NSFS_E_NOFIELD;
+    if (cap < 0) return NSFS_E_ARG;
+    long long dcap = cap;
+    if (dcap > h->N + 1) dcap = h->N + 1;
+    if (!path_ij) dcap = 0;
+    const size_t o_path = 256;
+    if ((rc = ensure_scratch(h, o_path + (size_t)dcap * 8 + 256)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    // header: int n @0, int status @4, double cost @8
+    if ((rc = launch_field_path(h, gi, gj, (int32_t*)(d + o_path), (int)dcap, (int*)d, (double*)(d + 8), (int*)(d + 4))) != NSFS_OK) return rc;
+    struct { int n, status; double cost; } hd;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&hd, d, sizeof(hd), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n_path) *n_path = hd.n;
+    if (cost) *cost = hd.cost;
+    const long long ncopy = hd.n < dcap ? hd.n : dcap;
+    if (path_ij && ncopy > 0) {
+        NSFS_CUDA_TRY(h, cudaMemcpyAsync(path_ij, d + o_path, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, h->stream));
+        NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return hd.status;
+}
+
+// ---- line of sight -------------------------------------------------------------------------------------------
+int nsfs_los_batch(nsfs_t* h, int n, const int32_t* seg4, int8_t* out) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (n < 0 || (n && (!seg4 || !out))) return NSFS_E_ARG;
+    if (!n) return NSFS_OK;
+    const size_t in_b = align_up((size_t)n * 16, 256);
+    if ((rc = ensure_scratch(h, in_b + n)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d, seg4, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_los_batch(h, n, (const int32_t*)d, (int8_t*)(d + in_b))) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(out, d + in_b, n, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+int nsfs_any_angle(nsfs_t* h, int n, const int32_t* pts_ij, uint8_t* keep) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (n < 1 || !pts_ij || !keep) return NSFS_E_ARG;
+    const size_t o_pts = 256, o_keep = align_up(o_pts + (size_t)n * 8, 256);
+    if ((rc = ensure_scratch(h, o_keep + n + 256)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d + o_pts, pts_ij, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_any_angle(h, n, (const int32_t*)(d + o_pts), (uint8_t*)(d + o_keep))) != NSFS_OK) return rc;
+    int status = 0;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&status, d, 4, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(keep, d + o_keep, n, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return status;
+}
+
+// ---- service ---------------------------------------------------------------------------------------------------
+int nsfs_sync(nsfs_t* h) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+long long nsfs_kernel_launches(const nsfs_t* h) { return h ? h->launches : 0; }
+void* nsfs_stream(nsfs_t* h) { return h ? (void*)h->stream : nullptr; }
+
+int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
+    if (!h || !key) return NSFS_E_ARG;
+    if (!strcmp(key, "max_slots")) { h->opt_max_slots = value; search_free(h); return NSFS_OK; }
+    if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
+    if (!strcmp(key, "field_tile_repeat")) { h->opt_field_tile_repeat = value; return NSFS_OK; }
+    return NSFS_E_ARG;
+}
+
+const char* nsfs_strerror(int code) {
+    switch (code) {
+        case NSFS_OK: return "ok";
+        case NSFS_E_RANGE: return "the reference would throw std::out_of_range (vector::at in testPos)";
+        case NSFS_E_CUDA: return "CUDA error (see nsfs_last_cuda_error); there is no CPU fallback";
+        case NSFS_E_TRUNC: return "output buffer too small";
+        case NSFS_E_ARG: return "bad argument";
+        case NSFS_E_NOMEM: return "out of memory";
+        case NSFS_E_HEAP: return "open list exceeded its device capacity";
+        case NSFS_E_NOMAP: return "no map set";
+        case NSFS_E_NOFIELD: return "no cost-to-go field computed on this handle";
+        default: return "unknown nsfs error";
+    }
+}
+
+const char* nsfs_last_cuda_error(const nsfs_t* h) { return h ? h->cuda_error : ""; }
+const char* nsfs_version(void) { return "nsfs-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Map ingestion: int32 inflation / log-odds planes -> bit planes + per-cell edge masks.
+//
+// Reference semantics restated here (never its code):
+//   free(k)  := infl[k] <= 0 && lo[k] <= lo_thresh                   testPos, grid_planner_core.cpp:434-455
+//   oob      := only the ROW is tested                                oob,     grid_planner_core.cpp:423-426
+//   neighbours are addressed by the flat key k + DI*W + DJ            flatten, grid_planner_core.cpp:404-407
+//   cost of direction d = 1 if an even number of passable directions precede it, else sqrt(2)
+//                                                                     astar.cpp:88,97-101,107,123
+#include "nsfs_internal.cuh"
+
+namespace nsfs {
+
+// ---- kernel 1: pack -------------------------------------------------------------------------------
+// Each thread reads 4 consecutive cells of both planes with one 128-bit load each (fully coalesced:
+// a warp covers 128 cells = 512 B per plane), forms a 4-bit nibble per plane, and 8 neighbouring lanes
+// OR their nibbles into one 32-bit word with three xor-shuffles.  HBM-bound: 8 B/cell in, 0.25 B/cell out.
+__global__ void __launch_bounds__(256) pack_map_kernel(const int32_t* __restrict__ infl, const int32_t* __restrict__ lo,
+                                                       int lo_thresh, long long N, uint32_t* __restrict__ free_bits,
+                                                       uint32_t* __restrict__ infl_bits, long long n_words) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 cells
+    const long long k0 = t * 4;
+    uint32_t fn = 0, in_ = 0;
+    if (k0 + 3 < N) {
+        const int4 a = __ldcs(reinterpret_cast<const int4*>(infl) + t);     // streamed once: evict-first
+        const int4 b = __ldcs(reinterpret_cast<const int4*>(lo) + t);
+        in_ = (a.x > 0) | ((a.y > 0) << 1) | ((a.z > 0) << 2) | ((a.w > 0) << 3);
+        const uint32_t occ = (b.x > lo_thresh) | ((b.y > lo_thresh) << 1) | ((b.z > lo_thresh) << 2) | ((b.w > lo_thresh) << 3);
+        fn = ~(in_ | occ) & 0xFu;
+    } else {
+        for (int c = 0; c < 4; ++c) {
+            const long long k = k0 + c;
+            if (k < N) {
+                const bool inf = infl[k] > 0;
+                const bool occ = lo[k] > lo_thresh;
+                in_ |= (uint32_t)inf << c;
+                fn |= (uint32_t)(!inf && !occ) << c;
+            }
+        }
+    }
+    const int sh = 4 * (threadIdx.x & 7);
+    fn <<= sh;
+    in_ <<= sh;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        fn |= __shfl_xor_sync(0xffffffffu, fn, m);
+        in_ |= __shfl_xor_sync(0xffffffffu, in_, m);
+    }
+    const long long w = t >> 3;
+    if ((threadIdx.x & 7) == 0 && w < n_words) {
+        free_bits[w] = fn;
+        infl_bits[w] = in_;
+    }
+}
+
+// ---- kernel 2: out-edge masks ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N,
+                                                       uint16_t* __restrict__ out_mask) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= N) return;
+    const int i = (int)(u / W);
+    uint32_t pass = 0, diag = 0, thr = 0, card = 1;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const int ni = i + nb_di(d);
+        if (ni < 0 || ni >= H) continue;                       // row guard; toggle untouched
+        const long long kv = u + nb_off(d, W);
+        if (kv < 0 || kv >= N) { thr = kThrowBit; continue; }  // vector::at would throw here
+        if (!bit_at(free_bits, kv)) continue;                  // blocked; toggle untouched
+        pass |= 1u << d;
+        if (!card) diag |= 1u << (8 + d);
+        card ^= 1u;
+    }
+    out_mask[u] = (uint16_t)(pass | diag | thr);
+}
+
+// ---- kernel 3: in-edge masks (pull form used by the field relaxation) --------------------------------
+__global__ void __launch_bounds__(256) in_mask_kernel(const uint32_t* __restrict__ free_bits,
+                                                      const uint16_t* __restrict__ out_mask, int H, int W, long long N,
+                                                      uint16_t* __restrict__ in_mask) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    uint32_t m = 0;
+    if (bit_at(free_bits, v)) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const long long u = v - nb_off(d, W);
+            if (u < 0 || u >= N) continue;
+            if (!bit_at(free_bits, u)) continue;               // only free cells are ever expanded (the source is seeded apart)
+            const uint32_t om = __ldg(out_mask + u);
+            if (!((om >> d) & 1u)) continue;                   // row guard of u failed for d
+            m |= 1u << d;
+            m |= ((om >> (8 + d)) & 1u & (uint32_t)(d != 0)) << (8 + d);
+        }
+    }
+    in_mask[v] = (uint16_t)m;
+}
+
+// ---- testPos for a batch of cells --------------------------------------------------------------------
+__global__ void test_pos_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N, int n,
+                                const int32_t* __restrict__ ij, int8_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = ij[2 * t], j = ij[2 * t + 1];
+    const long long key = (long long)i * W + j;
+    int8_t r;
+    if (i < 0 || i >= H) r = 0;
+    else if (key < 0 || key >= N) r = -1;
+    else r = bit_at(free_bits, key) ? 1 : 0;
+    out[t] = r;
+}
+
+int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo) {
+    const long long n_words = (h->N + 31) / 32;
+    const long long threads = n_words * 8;
+    const int block = 256;
+    const long long grid = (threads + block - 1) / block;
+    pack_map_kernel<<<(unsigned)grid, block, 0, h->stream>>>(d_infl, d_lo, h->lo_thresh, h->N, h->d_free, h->d_inflated, n_words);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+int launch_build_masks(nsfs_planner* h) {
+    const int block = 256;
+    const long long grid = (h->N + block - 1) / block;
+    out_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, h->d_out_mask);
+    in_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, h->d_in_mask);
+    h->launches += 2;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out) {
+    if (n <= 0) return NSFS_OK;
+    test_pos_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, n, d_ij, d_out);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+}  // namespace nsfs

@@ -1,0 +1,125 @@
+// Internal declarations shared by the sm_100a translation units of libnsfs_gpu.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nsfs.h"
+
+namespace nsfs {
+
+// ---- reference constants ---------------------------------------------------------------------------
+// NB_LUT order (reference grid_planner_core.h:197): d -> (DI, DJ); flat offset OFF[d] = DI*W + DJ.
+// Packed 2-bit tables (value + 1) so a run-time d costs a shift and a mask and a constant d folds away.
+__host__ __device__ __forceinline__ int nb_di(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }   // {1,1,0,-1,-1,-1,0,1}
+__host__ __device__ __forceinline__ int nb_dj(int d) { return (int)((0x01A9u >> (2 * d)) & 3u) - 1; }   // {0,1,1,1,0,-1,-1,-1}
+__host__ __device__ __forceinline__ long long nb_off(int d, int W) { return (long long)nb_di(d) * W + nb_dj(d); }
+
+constexpr float  kInfF = 1e5f;                 // "infinity" of the reference (astar.cpp:40)
+constexpr double kInfD = 1e5;
+constexpr double kSlack = 1e-5;                // relaxation slack (astar.cpp:116)
+constexpr double kSqrt2D = 1.41421356237309504880;
+constexpr float  kSqrt2F = 1.41421356237309504880f;
+
+// ---- per-cell edge masks ---------------------------------------------------------------------------
+// out_mask[u] (uint16): bits 0..7  pass[d]  : neighbour u+OFF[d] is reached by plan()'s loop (row guard ok,
+//                                             key in range, free)                    (astar.cpp:89-101)
+//                       bits 9..15 diag[d]  : that edge costs sqrt(2) (odd number of passable directions
+//                                             before d; is_cardinal toggle, astar.cpp:88,107,123); d = 0 is
+//                                             never diagonal, so
+//                       bit  8     throws   : some direction passes the row guard with a key outside [0,N)
+//                                             => vector::at throws when u is expanded
+// in_mask[v]  (uint16): bits 0..7  in-edge d exists from the FREE cell v-OFF[d]; bits 8..15 it costs sqrt(2)
+constexpr uint32_t kThrowBit = 1u << 8;
+
+struct FieldWork {
+    float*    g = nullptr;         // [N]
+    uint8_t*  pred = nullptr;      // [N]
+    uint8_t*  tile_flag = nullptr; // [nTiles] activation flags for the next round
+    int*      list[2] = {nullptr, nullptr};
+    int*      counts = nullptr;    // [8]: 0/1 list lengths, 2 rounds, 3 tile visits, 4 error flag, 5 reached
+    int       tiles_x = 0, tiles_y = 0;
+    int       src_i = -1, src_j = -1;
+    bool      valid = false;
+};
+
+struct SearchWork {
+    // one slot per concurrently running query (one warp each)
+    int       slots = 0;
+    long long heap_cap = 0;        // entries per slot
+    uint4*    cells = nullptr;     // [slots][N]   {g.lo, g.hi, parent key, (epoch << 1) | visited}
+    unsigned long long* heap = nullptr;  // [slots][heap_cap]
+    uint32_t* epoch = nullptr;     // [slots]
+    int*      work_counter = nullptr;
+};
+
+}  // namespace nsfs
+
+struct nsfs_planner {
+    int H = 0, W = 0;
+    long long N = 0;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int lo_thresh = 0;
+    bool have_map = false;
+    bool have_raw = false;          // d_infl / d_lo hold the int32 planes of the current map
+
+    int32_t*  d_infl = nullptr;     // staging for host maps [N]
+    int32_t*  d_lo = nullptr;
+    uint32_t* d_free = nullptr;     // bit k = free(k)            [(N+31)/32 + 4 words]
+    uint32_t* d_inflated = nullptr; // bit k = infl[k] > 0
+    uint16_t* d_out_mask = nullptr; // [N]
+    uint16_t* d_in_mask = nullptr;  // [N]
+
+    nsfs::FieldWork field;
+    nsfs::SearchWork search;
+
+    // small device scratch + pinned host mirror for per-call scalars/results
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    void* h_pinned = nullptr;  size_t pinned_bytes = 0;
+
+    long long launches = 0;
+    long long opt_max_slots = 0;        // 0 = auto
+    long long opt_heap_cap = 0;         // 0 = auto (N entries)
+    long long opt_field_tile_repeat = 1;
+    char cuda_error[256] = {0};
+};
+
+namespace nsfs {
+
+// Every launcher returns NSFS_OK or NSFS_E_CUDA and bumps h->launches by the kernels it launched.
+int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo);
+int launch_build_masks(nsfs_planner* h);
+int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out);
+
+int field_alloc(nsfs_planner* h);
+void field_free(nsfs_planner* h);
+int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
+int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap, int* d_n, double* d_cost, int* d_status);
+
+int search_alloc(nsfs_planner* h, int want_slots);
+void search_free(nsfs_planner* h);
+// kind: 0 plan (algo/mode), 1 find_better_point.  All pointers are device pointers; paths optional.
+int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* d_q,
+                  int32_t* d_status, double* d_g_goal, int32_t* d_path_len, long long* d_settled,
+                  int32_t* d_paths, int path_cap, long long* d_stats5);
+
+int launch_los_batch(nsfs_planner* h, int n, const int32_t* d_seg4, int8_t* d_out);
+int launch_any_angle(nsfs_planner* h, int n, const int32_t* d_pts, uint8_t* d_keep);
+
+int set_cuda_error(nsfs_planner* h, cudaError_t e, const char* where);
+
+#define NSFS_CUDA_TRY(h, expr)                                                      \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return ::nsfs::set_cuda_error((h), _e, #expr);       \
+    } while (0)
+
+// ---- device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ bool bit_at(const uint32_t* __restrict__ plane, long long k) {
+    return (__ldg(plane + (k >> 5)) >> (k & 31)) & 1u;
+}
+
+}  // namespace nsfs
