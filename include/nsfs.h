@@ -62,6 +62,7 @@ typedef struct nsfs_stats {
     long long tile_visits;   /* tile relaxations (field) */
     long long launches;      /* kernels launched by this call */
     float     gpu_ms;        /* device time of the call's kernels (CUDA events on the handle's stream) */
+    float     main_kernel_ms;/* device time of the call's dominant kernel alone (field_solve / search), same clock */
 } nsfs_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------

@@ -34,6 +34,11 @@ struct Timer {
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
         return ms;
     }
+    float main_kernel_ms() {     // valid after stop_sync(): ev2/ev3 bracket the dominant kernel on the same stream
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        return ms;
+    }
 };
 
 static int enter(nsfs_planner* h, bool need_map) {
@@ -82,6 +87,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
         cudaError_t e;
         if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+            (e = cudaEventCreate(&h->ev2)) != cudaSuccess || (e = cudaEventCreate(&h->ev3)) != cudaSuccess ||
             (e = cudaMalloc(&h->d_free, words * 4)) != cudaSuccess || (e = cudaMalloc(&h->d_inflated, words * 4)) != cudaSuccess ||
             (e = cudaMalloc(&h->d_out_mask, (size_t)N * 2)) != cudaSuccess || (e = cudaMalloc(&h->d_in_mask, (size_t)N * 2)) != cudaSuccess ||
             (e = cudaMemsetAsync(h->d_free, 0, words * 4, h->stream)) != cudaSuccess ||
@@ -107,6 +113,8 @@ void nsfs_destroy(nsfs_t* h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -175,11 +183,11 @@ int nsfs_test_pos_batch(nsfs_t* h, int n, const int32_t* ij, int8_t* out) {
 }
 
 // ---- searches ------------------------------------------------------------------------------------------
-static void fill_stats(nsfs_stats* st, const long long* s5, long long launches, float ms) {
+static void fill_stats(nsfs_stats* st, const long long* s5, long long launches, float ms, float main_ms) {
     if (!st) return;
     memset(st, 0, sizeof(*st));
     st->pops = s5[0]; st->expansions = s5[1]; st->pushes = s5[2]; st->heap_peak = s5[3]; st->los_checks = s5[4];
-    st->launches = launches; st->gpu_ms = ms;
+    st->launches = launches; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
 }
 
 // Runs nq queries given as host arrays; kind 0 = plan, 1 = find_better_point.  Retries open-list overflows once
@@ -220,7 +228,7 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     if (paths && path_elems) NSFS_CUDA_TRY(h, cudaMemcpyAsync(paths, d + o_paths, path_elems * 4, cudaMemcpyDeviceToHost, h->stream));
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (status) memcpy(status, stat_h.data(), (size_t)nq * 4);
-    fill_stats(st, s5, h->launches - launches0, ms);
+    fill_stats(st, s5, h->launches - launches0, ms, tm.main_kernel_ms());
 
     // ---- open-list overflow: redo those queries one at a time with the worst-case capacity ----------------
     const long long worst = 8 * h->N + 16;
@@ -310,7 +318,7 @@ int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int
         const float ms = tm.stop_sync();
         long long s5[5];
         NSFS_CUDA_TRY(h, cudaMemcpy(s5, d_s5, sizeof(s5), cudaMemcpyDeviceToHost));
-        fill_stats(st, s5, h->launches - launches0, ms);
+        fill_stats(st, s5, h->launches - launches0, ms, tm.main_kernel_ms());
     }
     return NSFS_OK;
 }
@@ -352,7 +360,7 @@ int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_
     if (st) {
         memset(st, 0, sizeof(*st));
         st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5]; st->pops = counts[6];
-        st->launches = h->launches - launches0; st->gpu_ms = ms;
+        st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = tm.main_kernel_ms();
     }
     if (d_g) *d_g = h->field.g;
     if (d_pred) *d_pred = h->field.pred;

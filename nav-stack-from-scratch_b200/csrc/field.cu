@@ -364,7 +364,9 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
     const int n_tiles = f.tiles_x * f.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
     void* args[] = {&p};
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
     NSFS_CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)field_solve_kernel, dim3(grid), dim3(FIELD_THREADS), args, 0, h->stream));
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     const long long ks = (long long)si * h->W + sj;
     field_pred_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f.g, h->d_in_mask, h->d_out_mask, h->W, h->N, ks,
                                                                              f.pred, f.counts);

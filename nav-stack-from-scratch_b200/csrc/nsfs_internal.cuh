@@ -61,7 +61,8 @@ struct nsfs_planner {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // whole call
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // dominant kernel of the call
     int lo_thresh = 0;
     bool have_map = false;
     bool have_raw = false;          // d_infl / d_lo hold the int32 planes of the current map

@@ -399,11 +399,13 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
     const int block = SEARCH_WARPS_PER_BLOCK * 32;
     const int grid = (p.slots + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK;
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
     if (kind == 1) { p.mode = NSFS_MODE_G; search_kernel<kAlgoFallback><<<grid, block, 0, h->stream>>>(p); }
     else if (algo == NSFS_ASTAR) search_kernel<NSFS_ASTAR><<<grid, block, 0, h->stream>>>(p);
     else if (algo == NSFS_DJIKSTRA) search_kernel<NSFS_DJIKSTRA><<<grid, block, 0, h->stream>>>(p);
     else if (algo == NSFS_THETASTAR) search_kernel<NSFS_THETASTAR><<<grid, block, 0, h->stream>>>(p);
     else return NSFS_E_ARG;
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;

@@ -29,7 +29,8 @@ class NsfsError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("pops", C.c_longlong), ("expansions", C.c_longlong), ("pushes", C.c_longlong),
                 ("heap_peak", C.c_longlong), ("los_checks", C.c_longlong), ("rounds", C.c_longlong),
-                ("tile_visits", C.c_longlong), ("launches", C.c_longlong), ("gpu_ms", C.c_float)]
+                ("tile_visits", C.c_longlong), ("launches", C.c_longlong), ("gpu_ms", C.c_float),
+                ("main_kernel_ms", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

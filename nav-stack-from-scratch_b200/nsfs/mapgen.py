@@ -96,8 +96,9 @@ def sample_queries(infl, lo, nq, seed, lo_thresh=LO_THRESH) -> np.ndarray:
 def sample_blocked_interior(infl, lo, n, seed, lo_thresh=LO_THRESH, margin=2) -> np.ndarray:
     """Non-free cells at least ``margin`` away from the border (inputs for find_better_point)."""
     m = ~free_mask(infl, lo, lo_thresh)
-    m[:margin, :] = m[-margin:, :] = False
-    m[:, :margin] = m[:, -margin:] = False
+    if margin > 0:
+        m[:margin, :] = m[-margin:, :] = False
+        m[:, :margin] = m[:, -margin:] = False
     return sample_cells(m, n, seed + 1)
 
 

@@ -118,7 +118,7 @@ class Oracle:
         return self.lib.nso_test_pos(C.byref(self.map), int(i), int(j))
 
     def bresenham(self, s, t, closed=False):
-        n = max(abs(t[0] - s[0]), abs(t[1] - s[1])) + 1
+        n = int(max(abs(int(t[0]) - int(s[0])), abs(int(t[1]) - int(s[1])))) + 1
         out = np.zeros((n, 2), np.int32)
         fn = self.lib.nso_bresenham_closed if closed else self.lib.nso_bresenham
         m = fn(int(s[0]), int(s[1]), int(t[0]), int(t[1]), out.ctypes.data_as(C.c_void_p), n)
@@ -250,7 +250,7 @@ class Reference:
         return self.lib.nsref_test_pos(self.ctx, int(i), int(j))
 
     def bresenham(self, s, t, closed=False):
-        n = max(abs(t[0] - s[0]), abs(t[1] - s[1])) + 1
+        n = int(max(abs(int(t[0]) - int(s[0])), abs(int(t[1]) - int(s[1])))) + 1
         out = np.zeros((n, 2), np.int32)
         m = self.lib.nsref_bresenham(int(s[0]), int(s[1]), int(t[0]), int(t[1]), out.ctypes.data_as(C.c_void_p), n)
         assert m == n
@@ -295,6 +295,14 @@ class Reference:
         n = self.lib.nsref_heap_trace(MODES[mode], len(ops), ops.ctypes.data_as(C.c_void_p),
                                       out.ctypes.data_as(C.c_void_p))
         return out[:n].copy()
+
+    def field_batch(self, srcs, nthreads=1):
+        srcs = np.ascontiguousarray(srcs, np.int32).reshape(-1, 2)
+        settled = np.zeros(len(srcs), np.int64)
+        sec = C.c_double(0)
+        rc = self.lib.nsref_field_batch(self.ctx, len(srcs), srcs.ctypes.data_as(C.c_void_p), int(nthreads),
+                                        settled.ctypes.data_as(C.c_void_p), C.byref(sec))
+        return dict(status=rc, settled=settled, seconds=sec.value)
 
     def plan_batch(self, algo, mode, sg4, nthreads=1):
         sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)

@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -335,6 +336,52 @@ int nsref_plan_batch(nsref_t* c, int algo, int mode, int nq, const int32_t* sg4,
                     if (g_goal) g_goal[q] = -1;
                     if (path_len) path_len[q] = -1;
                     if (settled) settled[q] = -1;
+                }
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    if (seconds) *seconds = now_s() - t0;
+    for (int s : status) if (s) return s;
+    return 0;
+}
+
+// The map generator's random stream as SURVEY.md §8d specifies it (std::mt19937 + uniform_real_distribution),
+// so tests can pin nsfs/mapgen.py (numpy) to the C++ definition.
+void nsref_uniform01(unsigned seed, int n, double* out) {
+    std::mt19937 g(seed);
+    std::uniform_real_distribution<double> u(0.0, 1.0);
+    for (int t = 0; t < n; ++t) out[t] = u(g);
+}
+void nsref_mt_raw(unsigned seed, int n, uint32_t* out) {
+    std::mt19937 g(seed);
+    for (int t = 0; t < n; ++t) out[t] = (uint32_t)g();
+}
+
+// n_src full Djikstra fields (plan() with an unreachable goal) spread over `nthreads` host threads, one planner
+// object per thread; used by bench.py --impl reference to load every host core with the reference's own code.
+// settled[s] = visited cells of field s.  Construction is outside the timed region.
+int nsref_field_batch(nsref_t* c, int n_src, const int32_t* src_ij, int nthreads, long long* settled, double* seconds) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > n_src) nthreads = n_src > 0 ? n_src : 1;
+    std::vector<std::unique_ptr<Djikstra>> ps(nthreads);
+    for (int t = 0; t < nthreads; ++t) ps[t] = std::make_unique<Djikstra>(std::string("g"), c->map);
+    std::vector<int> status(nthreads, 0);
+    double t0 = now_s();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t]() {
+            Djikstra* p = ps[t].get();
+            for (int s = t; s < n_src; s += nthreads) {
+                p->open_list_.size_ = 0;
+                p->open_list_.clearQ();
+                Index a(src_ij[2 * s], src_ij[2 * s + 1]), goal(-7, -7);
+                try {
+                    (void)p->plan(a, goal, c->map);
+                    if (settled) settled[s] = count_visited(p);
+                } catch (...) {
+                    status[t] = -1;
+                    if (settled) settled[s] = -1;
                 }
             }
         });

@@ -1,0 +1,156 @@
+"""CUDA path against the CPU oracle on seeded inputs sized so the oracle finishes in seconds."""
+import numpy as np
+import pytest
+
+from nsfs import mapgen
+
+pytestmark = pytest.mark.gpu
+
+ALGO_ID = {"astar": 0, "djikstra": 1, "thetastar": 2}
+
+
+def _planner(gpu_lib, infl, lo):
+    P = gpu_lib.Planner(*infl.shape)
+    P.set_map(infl, lo)
+    return P
+
+
+def _compare_batch(P, O, aname, mode, qs, cap):
+    b = P.plan_batch(aname, mode, qs, path_cap=cap)
+    for qi, q in enumerate(qs):
+        o = O.plan(ALGO_ID[aname], mode, q[:2], q[2:])
+        n = len(o["path"])
+        assert b["status"][qi] == o["status"] == 0
+        assert b["path_len"][qi] == n and np.array_equal(b["paths"][qi][:n], o["path"]), (aname, mode, qi)
+        assert b["g_goal"][qi] == o["g_goal"]            # same fp64 additions in the same order: bit-exact
+        assert b["settled"][qi] == o["settled"]
+    return b
+
+
+def test_c1_astar_384_inflated(gpu_lib, oracle_mod):
+    """BASELINE config 0: Astar on the 384x384 inflated map, f and fg."""
+    infl, lo = mapgen.synth_map(384, 384, 0.005, 1, inflated=True)
+    P, O = _planner(gpu_lib, infl, lo), oracle_mod.Oracle(infl, lo)
+    qs = mapgen.sample_queries(infl, lo, 48, 1)
+    for mode in ("f", "fg"):
+        b = _compare_batch(P, O, "astar", mode, qs, cap=2048)
+        assert b["stats"]["pops"] > 0
+    P.close()
+
+
+def test_djikstra_exact_and_thetastar(gpu_lib, oracle_mod):
+    infl, lo = mapgen.synth_map(200, 260, 0.12, 31)
+    P, O = _planner(gpu_lib, infl, lo), oracle_mod.Oracle(infl, lo)
+    qs = mapgen.sample_queries(infl, lo, 24, 31)
+    _compare_batch(P, O, "djikstra", "g", qs, cap=2048)
+    for mode in ("f", "fg", "g"):
+        b = _compare_batch(P, O, "thetastar", mode, qs, cap=2048)    # design oracle: parity unpinned vs the reference
+    assert b["stats"]["los_checks"] > 0
+    P.close()
+
+
+def test_field_512_and_predecessor_walk(gpu_lib, oracle_mod):
+    infl, lo = mapgen.synth_map(512, 512, 0.10, 41)
+    P, O = _planner(gpu_lib, infl, lo), oracle_mod.Oracle(infl, lo)
+    src = mapgen.field_source(infl, lo)
+    r, o = P.field(src), O.field(src)
+    reach = o["g"] < 1e5
+    assert np.array_equal(r["g"] < 1e5, reach) and r["reached"] == o["settled"]
+    rel = np.abs(r["g"].astype(np.float64) - o["g"])[reach] / np.maximum(o["g"][reach], 1.0)
+    assert rel.max() <= 1e-5
+    W = infl.shape[1]
+    free = mapgen.free_mask(infl, lo).reshape(-1)
+    for goal in mapgen.sample_free_cells(infl, lo, 16, 43):
+        fp = P.field_path(goal)
+        g_ref = o["g"][goal[0], goal[1]]
+        if g_ref >= 1e5:
+            assert fp["n_path"] == 1
+            continue
+        assert abs(fp["cost"] - g_ref) <= 1e-9 * max(g_ref, 1.0)      # fp64 recount along an optimal path
+        keys = fp["path"][:, 0] * W + fp["path"][:, 1]
+        assert np.isin(keys[:-1] - keys[1:], [W, W + 1, 1, -W + 1, -W, -W - 1, -1, W - 1]).all()
+        assert free[keys].all() and tuple(fp["path"][-1]) == tuple(src)
+    P.close()
+
+
+def test_non_square_ragged_tiles_and_blocked_source(gpu_lib, oracle_mod):
+    """Grid sides that are not multiples of the 64-cell tile, a source on a blocked cell, an isolated source."""
+    infl, lo = mapgen.synth_map(130, 197, 0.18, 51)
+    P, O = _planner(gpu_lib, infl, lo), oracle_mod.Oracle(infl, lo)
+    blocked = mapgen.sample_blocked_interior(infl, lo, 3, 51)
+    free = mapgen.sample_free_cells(infl, lo, 3, 52)
+    for src in list(blocked) + list(free):
+        r, o = P.field(src), O.field(src)
+        assert r["status"] == o["status"] == 0
+        reach = o["g"] < 1e5
+        assert np.array_equal(r["g"] < 1e5, reach)
+        rel = np.abs(r["g"].astype(np.float64) - o["g"])[reach] / np.maximum(o["g"][reach], 1.0)
+        assert rel.max() <= 1e-5
+    P.close()
+
+
+def test_unframed_map_wraps_columns_like_the_reference(gpu_lib, oracle_mod):
+    """No frame: the flat-key stencil lets paths cross from column W-1 to column 0 of a later row."""
+    infl, lo = mapgen.synth_map(70, 67, 0.05, 61, frame=False)
+    infl[0:2, :] = 1; infl[-2:, :] = 1          # keep the four throwing cells unreachable, leave the side columns open
+    P, O = _planner(gpu_lib, infl, lo), oracle_mod.Oracle(infl, lo)
+    src = (35, 33)
+    infl[src] = 0; lo[src] = 0
+    P.set_map(infl, lo); O = oracle_mod.Oracle(infl, lo)
+    r, o = P.field(src), O.field(src)
+    assert r["status"] == o["status"] == 0
+    reach = o["g"] < 1e5
+    assert np.array_equal(r["g"] < 1e5, reach)
+    rel = np.abs(r["g"].astype(np.float64) - o["g"])[reach] / np.maximum(o["g"][reach], 1.0)
+    assert rel.max() <= 1e-5
+    qs = mapgen.sample_queries(infl, lo, 16, 61)
+    _compare_batch(P, O, "astar", "f", qs, cap=1024)
+    P.close()
+
+
+def test_map_can_change_between_calls(gpu_lib, oracle_mod):
+    """The reference re-reads MapData on every call (global_planner.cpp:65-73 replaces the vectors)."""
+    infl, lo = mapgen.synth_map(96, 96, 0.10, 71)
+    P = _planner(gpu_lib, infl, lo)
+    q = mapgen.sample_queries(infl, lo, 1, 71)[0]
+    a = P.plan("astar", "f", q[:2], q[2:])
+    infl2, lo2 = mapgen.synth_map(96, 96, 0.02, 72)
+    infl2[tuple(q[:2])] = infl2[tuple(q[2:])] = 0; lo2[tuple(q[:2])] = lo2[tuple(q[2:])] = 0
+    P.set_map(infl2, lo2)
+    b = P.plan("astar", "f", q[:2], q[2:])
+    o = oracle_mod.Oracle(infl2, lo2).plan(0, "f", q[:2], q[2:])
+    assert np.array_equal(b["path"], o["path"]) and b["g_goal"] == o["g_goal"]
+    assert a["g_goal"] != b["g_goal"] or not np.array_equal(a["path"], b["path"])
+    P.close()
+
+
+def test_small_open_list_capacity_is_retried(gpu_lib, oracle_mod):
+    infl, lo = mapgen.synth_map(64, 64, 0.05, 81)
+    P = _planner(gpu_lib, infl, lo)
+    P.set_option("heap_cap", 16)
+    qs = mapgen.sample_queries(infl, lo, 4, 81)
+    O = oracle_mod.Oracle(infl, lo)
+    b = P.plan_batch("astar", "f", qs, path_cap=256)
+    for qi, q in enumerate(qs):
+        o = O.plan(0, "f", q[:2], q[2:])
+        assert b["status"][qi] == 0 and b["g_goal"][qi] == o["g_goal"] and b["path_len"][qi] == len(o["path"])
+    P.close()
+
+
+def test_device_resident_batch_entry_point(gpu_lib, oracle_mod):
+    import torch
+    infl, lo = mapgen.synth_map(128, 128, 0.10, 91)
+    P = gpu_lib.Planner(128, 128)
+    d_infl = torch.from_numpy(infl).cuda(); d_lo = torch.from_numpy(lo).cuda()
+    P.set_map_device(d_infl.data_ptr(), d_lo.data_ptr())
+    qs = mapgen.sample_queries(infl, lo, 32, 91)
+    d_q = torch.from_numpy(qs).cuda()
+    d_status = torch.zeros(32, dtype=torch.int32, device="cuda"); d_g = torch.zeros(32, dtype=torch.float64, device="cuda")
+    d_len = torch.zeros(32, dtype=torch.int32, device="cuda"); d_set = torch.zeros(32, dtype=torch.int64, device="cuda")
+    P.plan_batch_device("astar", "f", 32, d_q.data_ptr(), d_status.data_ptr(), d_g.data_ptr(), d_len.data_ptr(), d_set.data_ptr())
+    P.sync()
+    O = oracle_mod.Oracle(infl, lo)
+    for qi, q in enumerate(qs):
+        o = O.plan(0, "f", q[:2], q[2:])
+        assert d_status[qi].item() == 0 and d_g[qi].item() == o["g_goal"] and d_set[qi].item() == o["settled"]
+    P.close()
