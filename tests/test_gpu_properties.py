@@ -29,12 +29,11 @@ def test_c2_field_2048_is_a_fixed_point_and_matches_probe_count(gpu_lib):
     OFF = np.array([W, W + 1, 1, -W + 1, -W, -W - 1, -1, W - 1])
     k = np.nonzero(reach & (pred != 255))[0]
     par = k - OFF[pred[k]]
-    step = g[k] - g[par]
     # every reached cell hangs off a reached parent at exactly one fp32 step of cost 1 or sqrt(2)
     assert reach[par].all()
     is1 = g[k] == g[par] + np.float32(1.0)
     is2 = g[k] == g[par] + SQRT2F
-    assert (is1 | is2).all() and step.min() >= 1.0
+    assert (is1 | is2).all()
     assert (reach & (pred == 255)).sum() == 1            # only the source has no predecessor
     # Bellman: on a framed map every free neighbour u of a free cell v has an edge u -> v of cost <= sqrt(2),
     # so no reached neighbour may undercut v by more than that (np.roll's wrap only touches the blocked frame)
