@@ -1,0 +1,28 @@
+import sys, os, itertools
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'nav-stack-from-scratch_b200'))
+import numpy as np
+from nsfs import mapgen, capi
+H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+infl, lo = mapgen.synth_map(H, W, 0.10, 5)
+P = capi.Planner(H, W); P.set_map(infl, lo)
+src = mapgen.field_source(infl, lo)
+ref = None
+P.set_option('field_mode', int(os.environ.get('MODE', '0')))
+inners = [int(x) for x in os.environ.get('INNERS', '1,2,4,8').split(',')]
+deltas = [float(x) for x in os.environ.get('DELTAS', '16,32,64,128,1000000').split(',')]
+idles = [int(x) for x in os.environ.get('IDLES', '100').split(',')]
+alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
+for inner, delta, alpha, idle in itertools.product(inners, deltas, alphas, idles):
+    P.set_option('field_idle_ns', idle)
+    P.set_option('field_alpha', alpha)
+    P.set_option('field_inner', inner); P.set_option('field_delta', int(delta))
+    best = None
+    for _ in range(4):
+        r = P.field_device(src)
+        st = r['stats']
+        if best is None or st['gpu_ms'] < best['gpu_ms']: best = st
+    g = P.field(src)['g']
+    if ref is None: ref = g
+    same = np.array_equal(ref, g)
+    print(f"idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)

@@ -364,7 +364,8 @@ int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_
     }
     if (d_g) *d_g = h->field.g;
     if (d_pred) *d_pred = h->field.pred;
-    if (counts[4]) return NSFS_E_RANGE;     // a reached cell's expansion throws in the reference
+    if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }
+    if (counts[4] & 1) return NSFS_E_RANGE; // a reached cell's expansion throws in the reference
     h->field.valid = true;
     return NSFS_OK;
 }
@@ -451,7 +452,11 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!h || !key) return NSFS_E_ARG;
     if (!strcmp(key, "max_slots")) { h->opt_max_slots = value; search_free(h); return NSFS_OK; }
     if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
-    if (!strcmp(key, "field_tile_repeat")) { h->opt_field_tile_repeat = value; return NSFS_OK; }
+    if (!strcmp(key, "field_inner")) { h->opt_field_inner = value; return NSFS_OK; }
+    if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
+    if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
+    if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
+    if (!strcmp(key, "field_alpha")) { h->opt_field_alpha = value; return NSFS_OK; }
     return NSFS_E_ARG;
 }
 

@@ -35,7 +35,7 @@ constexpr uint32_t kThrowBit = 1u << 8;
 struct FieldWork {
     float*    g = nullptr;         // [N]
     uint8_t*  pred = nullptr;      // [N]
-    uint8_t*  tile_flag = nullptr; // [nTiles] activation flags for the next round
+    uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
     int*      list[2] = {nullptr, nullptr};
     int*      counts = nullptr;    // [8]: 0/1 list lengths, 2 rounds, 3 tile visits, 4 error flag, 5 reached
     int       tiles_x = 0, tiles_y = 0;
@@ -84,7 +84,11 @@ struct nsfs_planner {
     long long launches = 0;
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
-    long long opt_field_tile_repeat = 1;
+    long long opt_field_inner = 0;      // 0 = default (4)
+    long long opt_field_delta = 0;      // 0 = default (64)
+    long long opt_field_mode = 0;       // 0 = asynchronous tile scheduling, 1 = bulk-synchronous rounds
+    long long opt_field_idle_ns = 0;    // 0 = default (100)
+    long long opt_field_alpha = -1;     // percent; < 0 = default (100)
     char cuda_error[256] = {0};
 };
 
