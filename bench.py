@@ -276,7 +276,7 @@ def ours(args):
             return st.expansions
 
         h2d, d2h = 2 * H * W * 4 + 8, H * W * 4 + H * W
-        main_kernel = "field_solve_kernel"
+        main_kernel = "field_solve_async_kernel"
     else:
         nq = args.batch if args.workload == "c4" else 1
         if rank == 0:

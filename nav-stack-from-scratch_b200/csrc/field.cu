@@ -157,7 +157,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         bool did = false;
         const uint32_t due = reinterpret_cast<const volatile uint32_t*>(s_flag_)[warp];   // my four flags in one load
 #pragma unroll
-        for (int q = 0; q < SB_PER_WARP; ++q) {
+        for (int q = 0; q < SB_PER_WARP && due != 0u; ++q) {
             const int sb = warp + q * FIELD_WARPS;
             if (!((due >> (8 * q)) & 0xffu)) continue;                // warp-uniform
             if (counted_idle) {                                       // leave the idle count BEFORE consuming the flag
@@ -165,8 +165,8 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                 counted_idle = false;
             }
             __syncwarp();
-            if (lane == 0) s_flag[warp * SB_PER_WARP + q] = 0;
-            __threadfence_block();                                    // clear first, then read the neighbours
+            if (lane == 0) s_flag[warp * SB_PER_WARP + q] = 0;       // clear first, then read the neighbours (volatile: program order)
+            __syncwarp();
             const volatile float* c = s + soff[q];
             const uint32_t m = mask[q];
             uint32_t bits = 0, last = 0;
@@ -190,7 +190,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                 __syncwarp();                                         // this warp's stores are visible to its next pass
             }
             if (bits) {
-                __threadfence_block();                                // values first, then the flags that announce them
+                __syncwarp();                                         // values first, then the flags that announce them
                 if (lane < 9) {
                     // lane l decides for neighbour (dy, dx) = (l/3 - 1, l%3 - 1) whether a changed cell borders it
                     const int dy = lane / 3 - 1, dx = lane % 3 - 1;

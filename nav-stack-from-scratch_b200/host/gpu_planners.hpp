@@ -1,0 +1,123 @@
+// gpu_planners.hpp — B200 children of GridPlannerCore: GpuAstar, GpuDjikstra, GpuThetaStar.
+//
+// Each child overrides exactly what the reference's children override (astar.h:7-24, djikstra.h:9-32):
+//   plan(Index, Index, MapData&), plan(Pos2D, Pos2D, MapData&), post_process_path(vector<Pos2D>&, MapData&)
+// and GpuDjikstra adds find_better_point(Index|Pos2D, MapData&) (djikstra.h:29-31).  All search work is done by
+// libnsfs_gpu.so through the C-ABI of include/nsfs.h; what stays on the host is the double-precision index<->world
+// conversion (grid_planner_core.cpp:409-421) and the collinearity filter sparsifyPath (grid_planner_core.cpp:506-535),
+// both a few dozen flops per path.  There is no CPU search fallback: if the CUDA library cannot run, construction throws.
+//
+// Error behaviour mirrors the reference: an expansion that would make vector::at throw surfaces as
+// std::out_of_range; "no path" is the single start position; a failed fallback returns the input position.
+#pragma once
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "nsfs.h"
+#include "planner_iface.hpp"
+
+namespace nsfs_host {
+
+// When does the planner re-upload MapData?  The reference reads the caller's vectors afresh on every call
+// (global_planner.cpp:65-73 replaces them whenever a ROS message arrives), so EveryCall is the default.
+enum class MapSync { EveryCall, OnNotify };
+
+class GpuPlannerBase : public GridPlannerCore {
+public:
+    ~GpuPlannerBase() override;
+    // reference: GridPlannerCore::prepPlanner(cost_mode, map) (grid_planner_core.cpp:570-600)
+    void prepPlanner(std::string cost_mode, bot_utils::MapData& map_data);
+    void setMapSync(MapSync m) { sync_ = m; }
+    void notifyMapChanged() { dirty_ = true; }
+    void setDevice(int device) { device_ = device; }
+    const nsfs_stats& lastStats() const { return stats_; }
+
+protected:
+    GpuPlannerBase();
+    GpuPlannerBase(std::string cost_mode, bot_utils::MapData& map_data);
+
+    std::vector<bot_utils::Pos2D> post_process_path(std::vector<bot_utils::Pos2D>& raw_path, bot_utils::MapData& map_data) override;
+
+    // host-side helpers restating grid_planner_core.cpp:409-421 and 506-535 in double
+    bot_utils::Index toIndex(const bot_utils::Pos2D& pos) const;
+    bot_utils::Pos2D toPos(int i, int j) const;
+    static std::vector<bot_utils::Pos2D> sparsify(const std::vector<bot_utils::Pos2D>& path_world);
+
+    void ensureHandle(bot_utils::MapData& map_data);
+    void uploadMap(bot_utils::MapData& map_data);
+    std::vector<bot_utils::Pos2D> runPlan(int algo, bot_utils::Index s, bot_utils::Index g, bot_utils::MapData& map_data);
+    static int modeCode(const std::string& cost_mode);
+    [[noreturn]] void fail(int code, const char* where) const;
+
+    nsfs_t* handle_ = nullptr;
+    int device_ = 0;
+    MapSync sync_ = MapSync::EveryCall;
+    bool dirty_ = true;
+    nsfs_stats stats_{};
+    std::vector<int32_t> path_buf_;
+#ifdef NSFS_USE_REFERENCE_HEADERS
+    // the reference base class already owns map_height_, map_width_, cell_size_, map_origin_, cost_mode_
+#endif
+};
+
+class GpuAstar : public GpuPlannerBase {
+public:
+    GpuAstar() = default;
+    GpuAstar(std::string cost_mode, bot_utils::MapData& map_data) : GpuPlannerBase(std::move(cost_mode), map_data) {}
+protected:
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
+};
+
+class GpuDjikstra : public GpuPlannerBase {
+public:
+    // Backend::Exact replays the reference's open-list order (identical path); Backend::Field relaxes the whole
+    // cost-to-go field in parallel (identical reachability and cost, possibly another equal-cost path; much faster
+    // on large maps).  Field falls back to Exact only where the reference's behaviour is order dependent (a cell whose
+    // expansion throws is reachable), never to the CPU.
+    enum class Backend { Exact, Field };
+    GpuDjikstra() = default;
+    GpuDjikstra(std::string cost_mode, bot_utils::MapData& map_data, Backend b = Backend::Exact)
+        : GpuPlannerBase(std::move(cost_mode), map_data), backend_(b) {}
+    void setBackend(Backend b) { backend_ = b; }
+    bot_utils::Pos2D find_better_point(bot_utils::Index idx_bad, bot_utils::MapData& map_data);
+    bot_utils::Pos2D find_better_point(bot_utils::Pos2D pos_bad, bot_utils::MapData& map_data);
+protected:
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
+private:
+    Backend backend_ = Backend::Exact;
+};
+
+// The reference ships no ThetaStar (thetastar.cpp is empty, thetastar.h:4-7 an empty class, the selection branch is
+// commented out at global_planner.cpp:116-119).  This child is Basic Theta* assembled from the reference's own
+// primitives (OpenList order, testPos, isLos/bresenham_los, dist_euc); DESIGN.md states the rule.
+class GpuThetaStar : public GpuPlannerBase {
+public:
+    GpuThetaStar() = default;
+    GpuThetaStar(std::string cost_mode, bot_utils::MapData& map_data) : GpuPlannerBase(std::move(cost_mode), map_data) {}
+protected:
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
+    std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
+};
+
+// ---- runtime selection (global_planner.cpp:102-130, 482-490) --------------------------------------------------
+struct PlannerConfig {
+    std::string planner_name = "astar";   // "astar" | "djikstra" | "thetastar"; anything else => astar (global_planner.cpp:121-125)
+    std::string cost_mode = "fg";         // "f" | "g" | "fg"; anything else => fg (grid_planner_core.cpp:274-281)
+    std::string djikstra_backend = "exact";  // "exact" | "field"
+    double gp_rate = 25.0;
+    bool verbose_planner = false;
+    int device = 0;
+};
+// Reads the planner keys of a rosparam-style YAML (flat "key: value" lines; core_turtle_config.yaml:33-36).
+PlannerConfig load_planner_config(const std::string& yaml_path);
+// GlobalPlanner::setupPlanner's choice (global_planner.cpp:102-125) with the GPU children.
+std::shared_ptr<GridPlannerCore> make_main_planner(const PlannerConfig& cfg, bot_utils::MapData& map_data);
+// The fallback planner: a Djikstra prepared with cost mode "g" (global_planner.cpp:127-128).
+std::shared_ptr<GpuDjikstra> make_fallback_planner(const PlannerConfig& cfg, bot_utils::MapData& map_data);
+
+}  // namespace nsfs_host
