@@ -1,0 +1,391 @@
+// gpu_planners.cpp — B200 children of GridPlannerCore (see gpu_planners.hpp) and a small C shim for the tests.
+//
+// Host-side work kept here, all in double like the reference:
+//   pos2idx / idx2pos         grid_planner_core.cpp:409-421
+//   sparsifyPath              grid_planner_core.cpp:506-535 (collinearity filter, |cross| > 1e-5)
+//   post_process_path         astar.cpp:150-165 == djikstra.cpp:147-163  (<= 2 points: unchanged)
+// Everything that searches the grid (plan, find_better_point, the isLos loop of makeAnyAnglePath) is a call into
+// libnsfs_gpu.so.  No CPU search exists in this file.
+#include "gpu_planners.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace nsfs_host {
+
+using bot_utils::Index;
+using bot_utils::MapData;
+using bot_utils::Pos2D;
+
+// ---- GpuPlannerBase ----------------------------------------------------------------------------------------
+GpuPlannerBase::GpuPlannerBase() : GridPlannerCore() {
+    // reference default ctor (grid_planner_core.cpp:341-351): cost mode "f", geometry unset until prepPlanner
+    cost_mode_ = "f";
+    map_height_ = 0; map_width_ = 0; cell_size_ = 0.0;
+}
+
+// Deliberately NOT GridPlannerCore(cost_mode, map): that ctor allocates the 40-byte-per-cell CPU Node store
+// (grid_planner_core.cpp:353-383), which the GPU planners never touch.
+GpuPlannerBase::GpuPlannerBase(std::string cost_mode, MapData& map_data) : GridPlannerCore() {
+    prepPlanner(std::move(cost_mode), map_data);
+}
+
+GpuPlannerBase::~GpuPlannerBase() {
+    if (handle_) nsfs_destroy(handle_);
+    handle_ = nullptr;
+}
+
+void GpuPlannerBase::prepPlanner(std::string cost_mode, MapData& map_data) {
+    cost_mode_ = std::move(cost_mode);
+    map_height_ = map_data.map_size_.i;
+    map_width_ = map_data.map_size_.j;
+    cell_size_ = map_data.cell_size_;
+    map_origin_.setCoords(map_data.origin_.x, map_data.origin_.y);
+    if (handle_) { nsfs_destroy(handle_); handle_ = nullptr; }
+    dirty_ = true;
+    ensureHandle(map_data);
+}
+
+[[noreturn]] void GpuPlannerBase::fail(int code, const char* where) const {
+    if (code == NSFS_E_RANGE)     // the reference's vector::at inside testPos (grid_planner_core.cpp:434-455)
+        throw std::out_of_range(std::string("vector::_M_range_check (testPos) in ") + where);
+    std::string msg = std::string(where) + ": " + nsfs_strerror(code);
+    if (code == NSFS_E_CUDA && handle_) msg += std::string(" | ") + nsfs_last_cuda_error(handle_);
+    throw std::runtime_error(msg);
+}
+
+void GpuPlannerBase::ensureHandle(MapData& map_data) {
+    if (handle_) return;
+    if (map_height_ <= 0 || map_width_ <= 0) {
+        map_height_ = map_data.map_size_.i;
+        map_width_ = map_data.map_size_.j;
+        cell_size_ = map_data.cell_size_;
+        map_origin_.setCoords(map_data.origin_.x, map_data.origin_.y);
+    }
+    const int rc = nsfs_create(&handle_, map_height_, map_width_, device_);
+    if (rc != NSFS_OK) { handle_ = nullptr; fail(rc, "nsfs_create"); }
+    dirty_ = true;
+}
+
+void GpuPlannerBase::uploadMap(MapData& map_data) {
+    ensureHandle(map_data);
+    if (sync_ == MapSync::OnNotify && !dirty_) return;
+    const size_t n = (size_t)map_height_ * (size_t)map_width_;
+    if (map_data.grid_inflation_.size() < n || map_data.grid_logodds_.size() < n)
+        throw std::out_of_range("MapData grids are smaller than map_size_");       // what .at() would report
+    static_assert(sizeof(int) == sizeof(int32_t), "MapData stores int planes");
+    const int rc = nsfs_set_map(handle_, reinterpret_cast<const int32_t*>(map_data.grid_inflation_.data()),
+                                reinterpret_cast<const int32_t*>(map_data.grid_logodds_.data()), map_data.lo_thresh_);
+    if (rc != NSFS_OK) fail(rc, "nsfs_set_map");
+    dirty_ = false;
+}
+
+Index GpuPlannerBase::toIndex(const Pos2D& pos) const {
+    const int i = (int)std::round((pos.x - map_origin_.x) / cell_size_);
+    const int j = (int)std::round((pos.y - map_origin_.y) / cell_size_);
+    return Index(i, j);
+}
+
+Pos2D GpuPlannerBase::toPos(int i, int j) const {
+    return Pos2D(i * cell_size_ + map_origin_.x, j * cell_size_ + map_origin_.y);
+}
+
+int GpuPlannerBase::modeCode(const std::string& cost_mode) {
+    if (cost_mode == "f") return NSFS_MODE_F;
+    if (cost_mode == "g") return NSFS_MODE_G;
+    return NSFS_MODE_FG;                              // unknown => fg (grid_planner_core.cpp:274-281)
+}
+
+std::vector<Pos2D> GpuPlannerBase::sparsify(const std::vector<Pos2D>& path_world) {
+    if (path_world.size() <= 2) return path_world;
+    std::vector<Pos2D> turning{path_world.front()};
+    for (size_t n = 2; n < path_world.size(); ++n) {
+        const Pos2D& nx = path_world[n];
+        const Pos2D& cu = path_world[n - 1];
+        const Pos2D& pv = path_world[n - 2];
+        const double dxn = nx.x - cu.x, dyn = nx.y - cu.y, dxp = cu.x - pv.x, dyp = cu.y - pv.y;
+        if (std::fabs(dxn * dyp - dyn * dxp) > 1e-5) turning.push_back(cu);
+    }
+    turning.push_back(path_world.back());
+    return turning;
+}
+
+std::vector<Pos2D> GpuPlannerBase::post_process_path(std::vector<Pos2D>& raw_path, MapData& map_data) {
+    if (raw_path.size() <= 2) return raw_path;
+    std::vector<Pos2D> tp = sparsify(raw_path);
+    // makeAnyAnglePath (grid_planner_core.cpp:537-558): the greedy isLos chain runs on the device
+    const int n = (int)tp.size();
+    if (n <= 2) return tp;
+    ensureHandle(map_data);
+    std::vector<int32_t> ij(2 * (size_t)n);
+    for (int t = 0; t < n; ++t) { const Index id = toIndex(tp[t]); ij[2 * t] = id.i; ij[2 * t + 1] = id.j; }
+    std::vector<uint8_t> keep((size_t)n, 0);
+    const int rc = nsfs_any_angle(handle_, n, ij.data(), keep.data());
+    if (rc != NSFS_OK) fail(rc, "nsfs_any_angle");
+    std::vector<Pos2D> out;
+    for (int t = 0; t < n; ++t) if (keep[t]) out.push_back(tp[t]);
+    return out;
+}
+
+std::vector<Pos2D> GpuPlannerBase::runPlan(int algo, Index s, Index g, MapData& map_data) {
+    uploadMap(map_data);
+    if (s.i < 0 || s.i >= map_height_ || s.j < 0 || s.j >= map_width_)
+        throw std::out_of_range("start index outside the node store");     // nodes[key] is undefined behaviour upstream
+    if (path_buf_.empty()) path_buf_.resize(2 * (size_t)(4 * (map_height_ + map_width_) + 64));
+    int n = 0;
+    double g_goal = 0.0;
+    int rc = nsfs_plan(handle_, algo, modeCode(cost_mode_), s.i, s.j, g.i, g.j, path_buf_.data(), (int)(path_buf_.size() / 2), &n,
+                       &g_goal, &stats_);
+    if (rc == NSFS_E_TRUNC) {              // path longer than the buffer: now its exact length is known
+        path_buf_.resize(2 * (size_t)n);
+        rc = nsfs_plan(handle_, algo, modeCode(cost_mode_), s.i, s.j, g.i, g.j, path_buf_.data(), n, &n, &g_goal, &stats_);
+    }
+    if (rc != NSFS_OK) fail(rc, "nsfs_plan");
+    last_g_goal_ = g_goal;
+    std::vector<Pos2D> path_world;
+    path_world.reserve((size_t)n);
+    for (int t = 0; t < n; ++t) path_world.push_back(toPos(path_buf_[2 * t], path_buf_[2 * t + 1]));
+    return path_world;
+}
+
+// ---- children ---------------------------------------------------------------------------------------------
+std::vector<Pos2D> GpuAstar::plan(Index idx_start, Index idx_goal, MapData& map_data) { return runPlan(NSFS_ASTAR, idx_start, idx_goal, map_data); }
+std::vector<Pos2D> GpuAstar::plan(Pos2D pos_start, Pos2D pos_goal, MapData& map_data) {
+    return plan(toIndex(pos_start), toIndex(pos_goal), map_data);       // astar.cpp:19-25
+}
+
+std::vector<Pos2D> GpuDjikstra::plan(Index idx_start, Index idx_goal, MapData& map_data) {
+    if (backend_ == Backend::Field) {
+        try {
+            return runPlan(NSFS_DJIKSTRA_FIELD, idx_start, idx_goal, map_data);
+        } catch (const std::out_of_range&) {
+            // a reachable cell's expansion throws in the reference; whether that happens before the goal is popped
+            // depends on the pop order, so let the exact-order search decide (still on the GPU)
+        }
+    }
+    return runPlan(NSFS_DJIKSTRA, idx_start, idx_goal, map_data);
+}
+std::vector<Pos2D> GpuDjikstra::plan(Pos2D pos_start, Pos2D pos_goal, MapData& map_data) {
+    return plan(toIndex(pos_start), toIndex(pos_goal), map_data);       // djikstra.cpp:19-25
+}
+
+Pos2D GpuDjikstra::find_better_point(Index idx_bad, MapData& map_data) {
+    uploadMap(map_data);
+    if (idx_bad.i < 0 || idx_bad.i >= map_height_ || idx_bad.j < 0 || idx_bad.j >= map_width_)
+        throw std::out_of_range("bad index outside the node store");
+    int fi = idx_bad.i, fj = idx_bad.j;
+    const int rc = nsfs_find_better_point(handle_, idx_bad.i, idx_bad.j, &fi, &fj, &stats_);
+    if (rc != NSFS_OK) fail(rc, "nsfs_find_better_point");
+    return toPos(fi, fj);
+}
+Pos2D GpuDjikstra::find_better_point(Pos2D pos_bad, MapData& map_data) {
+    return find_better_point(toIndex(pos_bad), map_data);               // djikstra.cpp:275-280
+}
+
+std::vector<Pos2D> GpuThetaStar::plan(Index idx_start, Index idx_goal, MapData& map_data) { return runPlan(NSFS_THETASTAR, idx_start, idx_goal, map_data); }
+std::vector<Pos2D> GpuThetaStar::plan(Pos2D pos_start, Pos2D pos_goal, MapData& map_data) {
+    return plan(toIndex(pos_start), toIndex(pos_goal), map_data);
+}
+
+// ---- runtime selection --------------------------------------------------------------------------------------
+static std::string trim(std::string s) {
+    const char* ws = " \t\r\n";
+    const size_t a = s.find_first_not_of(ws);
+    if (a == std::string::npos) return "";
+    const size_t b = s.find_last_not_of(ws);
+    s = s.substr(a, b - a + 1);
+    if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) s = s.substr(1, s.size() - 2);
+    return s;
+}
+
+PlannerConfig load_planner_config(const std::string& yaml_path) {
+    PlannerConfig cfg;
+    std::ifstream in(yaml_path);
+    if (!in) throw std::runtime_error("cannot open " + yaml_path);
+    std::string line;
+    while (std::getline(in, line)) {
+        // strip a trailing comment that is not inside quotes
+        bool q1 = false, q2 = false;
+        for (size_t c = 0; c < line.size(); ++c) {
+            if (line[c] == '"' && !q1) q2 = !q2;
+            else if (line[c] == '\'' && !q2) q1 = !q1;
+            else if (line[c] == '#' && !q1 && !q2) { line.resize(c); break; }
+        }
+        const size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        const std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+        if (val.empty()) continue;
+        if (key == "planner_name") cfg.planner_name = val;
+        else if (key == "cost_mode") cfg.cost_mode = val;
+        else if (key == "djikstra_backend") cfg.djikstra_backend = val;
+        else if (key == "gp_rate") cfg.gp_rate = std::atof(val.c_str());
+        else if (key == "verbose_planner") cfg.verbose_planner = (val == "true" || val == "True" || val == "1");
+        else if (key == "gpu_device") cfg.device = std::atoi(val.c_str());
+    }
+    return cfg;
+}
+
+std::shared_ptr<GridPlannerCore> make_main_planner(const PlannerConfig& cfg, MapData& map_data) {
+    // GlobalPlanner::setupPlanner (global_planner.cpp:102-125): astar | djikstra | (thetastar) | anything else => astar
+    if (cfg.planner_name == "djikstra") {
+        if (cfg.cost_mode != "g") fprintf(stderr, "[GlobalPlanner]: Djikstra requires g cost. f/fg is set. Planner is guaranteed to fail\n");
+        auto p = std::make_shared<GpuDjikstra>();
+        p->setDevice(cfg.device);
+        p->setBackend(cfg.djikstra_backend == "field" ? GpuDjikstra::Backend::Field : GpuDjikstra::Backend::Exact);
+        p->prepPlanner(cfg.cost_mode, map_data);
+        return p;
+    }
+    if (cfg.planner_name == "thetastar") {     // the branch the reference left commented out (global_planner.cpp:116-119)
+        auto p = std::make_shared<GpuThetaStar>();
+        p->setDevice(cfg.device);
+        p->prepPlanner(cfg.cost_mode, map_data);
+        return p;
+    }
+    if (cfg.cost_mode == "g") fprintf(stderr, "[GlobalPlanner]: Astar requires f/fg cost. g cost is set. Planner is guaranteed to fail\n");
+    auto p = std::make_shared<GpuAstar>();
+    p->setDevice(cfg.device);
+    p->prepPlanner(cfg.cost_mode, map_data);
+    return p;
+}
+
+std::shared_ptr<GpuDjikstra> make_fallback_planner(const PlannerConfig& cfg, MapData& map_data) {
+    auto p = std::make_shared<GpuDjikstra>();
+    p->setDevice(cfg.device);
+    p->prepPlanner("g", map_data);             // global_planner.cpp:127-128
+    return p;
+}
+
+}  // namespace nsfs_host
+
+// ---- C shim: lets the Python tests drive the C++ children exactly as GlobalPlanner::run would -----------------
+// (global_planner.cpp:183/212/234/271 generatePath, 191/225/244/247 find_better_point).  Test plumbing for the
+// adapter layer; the product boundary is include/nsfs.h.
+namespace {
+struct Session {
+    bot_utils::MapData map;
+    nsfs_host::PlannerConfig cfg;
+    std::shared_ptr<GridPlannerCore> main_planner;
+    std::shared_ptr<nsfs_host::GpuDjikstra> fallback;
+    std::string error;
+};
+// public generatePath is reachable through the base; plan() is protected, so raw plans go through this accessor
+template <class P> struct Raw : P { using P::plan; };
+}  // namespace
+
+extern "C" {
+
+// returns 0 ok, 1 std::out_of_range, 2 any other exception (text via nsfsh_error)
+void* nsfsh_create(const char* planner_name, const char* cost_mode, const char* djikstra_backend, int H, int W, double cell,
+                   double ox, double oy, int lo_thresh, const int32_t* infl, const int32_t* lo, int device, int* rc_out) {
+    auto* s = new Session();
+    int rc = 0;
+    try {
+        s->cfg.planner_name = planner_name ? planner_name : "astar";
+        s->cfg.cost_mode = cost_mode ? cost_mode : "fg";
+        s->cfg.djikstra_backend = djikstra_backend ? djikstra_backend : "exact";
+        s->cfg.device = device;
+        s->map.map_size_.setIdx(H, W);
+        s->map.cell_size_ = cell;
+        s->map.origin_.setCoords(ox, oy);
+        s->map.lo_thresh_ = lo_thresh;
+        s->map.total_cells_ = H * W;
+        s->map.grid_inflation_.assign(infl, infl + (size_t)H * W);
+        s->map.grid_logodds_.assign(lo, lo + (size_t)H * W);
+        s->main_planner = nsfs_host::make_main_planner(s->cfg, s->map);
+        s->fallback = nsfs_host::make_fallback_planner(s->cfg, s->map);
+    } catch (const std::out_of_range& e) { s->error = e.what(); rc = 1; }
+    catch (const std::exception& e) { s->error = e.what(); rc = 2; }
+    if (rc_out) *rc_out = rc;
+    return s;
+}
+
+void nsfsh_destroy(void* p) { delete static_cast<Session*>(p); }
+const char* nsfsh_error(void* p) { return p ? static_cast<Session*>(p)->error.c_str() : ""; }
+
+int nsfsh_set_map(void* p, const int32_t* infl, const int32_t* lo) {
+    auto* s = static_cast<Session*>(p);
+    const size_t n = (size_t)s->map.map_size_.i * s->map.map_size_.j;
+    s->map.grid_inflation_.assign(infl, infl + n);      // what the ROS callbacks do (global_planner.cpp:65-73)
+    s->map.grid_logodds_.assign(lo, lo + n);
+    return 0;
+}
+
+static int emit(const std::vector<bot_utils::Pos2D>& path, double* out_xy, int cap, int* n) {
+    if (n) *n = (int)path.size();
+    for (size_t t = 0; t < path.size() && (int)t < cap; ++t) { out_xy[2 * t] = path[t].x; out_xy[2 * t + 1] = path[t].y; }
+    return 0;
+}
+
+int nsfsh_generate_path_idx(void* p, int si, int sj, int gi, int gj, double* out_xy, int cap, int* n) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        bot_utils::Index a(si, sj), b(gi, gj);
+        return emit(s->main_planner->generatePath(a, b, s->map), out_xy, cap, n);
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+int nsfsh_generate_path_pos(void* p, double sx, double sy, double gx, double gy, double* out_xy, int cap, int* n) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        bot_utils::Pos2D a(sx, sy), b(gx, gy);
+        return emit(s->main_planner->generatePath(a, b, s->map), out_xy, cap, n);
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+int nsfsh_find_better_point_pos(void* p, double x, double y, double* fx, double* fy) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        const bot_utils::Pos2D r = s->fallback->find_better_point(bot_utils::Pos2D(x, y), s->map);
+        *fx = r.x; *fy = r.y;
+        return 0;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+int nsfsh_find_better_point_idx(void* p, int bi, int bj, double* fx, double* fy) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        const bot_utils::Pos2D r = s->fallback->find_better_point(bot_utils::Index(bi, bj), s->map);
+        *fx = r.x; *fy = r.y;
+        return 0;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+// Parses a rosparam-style YAML; strings are copied into 32-byte buffers.
+int nsfsh_load_config(const char* yaml_path, char* planner_name, char* cost_mode, char* djikstra_backend, double* gp_rate,
+                      int* verbose, int* device) {
+    try {
+        const nsfs_host::PlannerConfig c = nsfs_host::load_planner_config(yaml_path);
+        snprintf(planner_name, 32, "%s", c.planner_name.c_str());
+        snprintf(cost_mode, 32, "%s", c.cost_mode.c_str());
+        snprintf(djikstra_backend, 32, "%s", c.djikstra_backend.c_str());
+        *gp_rate = c.gp_rate; *verbose = c.verbose_planner ? 1 : 0; *device = c.device;
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+// Which child did setupPlanner's rule pick?  0 astar, 1 djikstra, 2 thetastar
+int nsfsh_main_planner_kind(void* p) {
+    auto* s = static_cast<Session*>(p);
+    if (dynamic_cast<nsfs_host::GpuDjikstra*>(s->main_planner.get())) return 1;
+    if (dynamic_cast<nsfs_host::GpuThetaStar*>(s->main_planner.get())) return 2;
+    return 0;
+}
+
+// sparsifyPath alone (host arithmetic; no device needed): lets the CPU suite check it against the golden finals' inputs
+int nsfsh_sparsify(const double* xy_in, int n_in, double* xy_out, int cap) {
+    struct Access : nsfs_host::GpuAstar { using nsfs_host::GpuPlannerBase::sparsify; };
+    std::vector<bot_utils::Pos2D> in;
+    for (int t = 0; t < n_in; ++t) in.emplace_back(xy_in[2 * t], xy_in[2 * t + 1]);
+    const auto out = Access::sparsify(in);
+    for (size_t t = 0; t < out.size() && (int)t < cap; ++t) { xy_out[2 * t] = out[t].x; xy_out[2 * t + 1] = out[t].y; }
+    return (int)out.size();
+}
+
+}  // extern "C"

@@ -34,6 +34,7 @@ public:
     void notifyMapChanged() { dirty_ = true; }
     void setDevice(int device) { device_ = device; }
     const nsfs_stats& lastStats() const { return stats_; }
+    double lastGoalCost() const { return last_g_goal_; }   // nodes[goal].g of the last plan (1e5 = unreachable)
 
 protected:
     GpuPlannerBase();
@@ -57,6 +58,7 @@ protected:
     MapSync sync_ = MapSync::EveryCall;
     bool dirty_ = true;
     nsfs_stats stats_{};
+    double last_g_goal_ = 0.0;
     std::vector<int32_t> path_buf_;
 #ifdef NSFS_USE_REFERENCE_HEADERS
     // the reference base class already owns map_height_, map_width_, cell_size_, map_origin_, cost_mode_

@@ -15,6 +15,7 @@
 #include "grid_planner_core.h"
 #else
 
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -70,9 +71,18 @@ public:
         auto raw = plan(idx_start, idx_goal, map_data);
         return post_process_path(raw, map_data);
     }
+    // grid_planner_core.cpp:610-615: positions are converted with pos2idx, then the Index overload runs
     std::vector<bot_utils::Pos2D> generatePath(bot_utils::Pos2D& pos_start, bot_utils::Pos2D& pos_goal, bot_utils::MapData& map_data) {
-        auto raw = plan(pos_start, pos_goal, map_data);
-        return post_process_path(raw, map_data);
+        bot_utils::Index a = pos2idx(pos_start), b = pos2idx(pos_goal);
+        return generatePath(a, b, map_data);
+    }
+
+protected:
+    // grid_planner_core.cpp:409-414
+    bot_utils::Index pos2idx(bot_utils::Pos2D& pos) {
+        const int i = (int)std::round((pos.x - map_origin_.x) / cell_size_);
+        const int j = (int)std::round((pos.y - map_origin_.y) / cell_size_);
+        return bot_utils::Index(i, j);
     }
 };
 

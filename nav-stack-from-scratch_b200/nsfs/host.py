@@ -1,0 +1,142 @@
+"""ctypes front-end of the C++ planner children (host/gpu_planners.cpp) through their nsfsh_* test shim.
+
+``Session`` is what GlobalPlanner holds (reference global_planner.h:52-53): a main planner picked by
+planner_name / cost_mode and a Djikstra fallback prepared with cost mode "g".  Two builds expose the same shim:
+  libnsfs_planners.so            the in-repo build against the interface mirror (host/planner_iface.hpp)
+  oracle/_ref/libnsfs_dropin.so  the same children compiled against the reference's OWN grid_planner_core.h
+                                 (built only where /root/reference exists; pass dropin=True)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(PKG)
+HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
+DROPIN_SO = os.path.join(ROOT, "oracle", "_ref", "libnsfs_dropin.so")
+
+SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
+           "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
+           "nsfsh_main_planner_kind", "nsfsh_sparsify")
+
+_libs = {}
+
+
+def lib(dropin=False):
+    path = DROPIN_SO if dropin else HOST_SO
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built")
+        L = C.CDLL(path)
+        vp, i32, dbl = C.c_void_p, C.c_int, C.c_double
+        L.nsfsh_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, dbl, dbl, dbl, i32, vp, vp, i32, C.POINTER(i32)]
+        L.nsfsh_create.restype = vp
+        L.nsfsh_destroy.argtypes = [vp]
+        L.nsfsh_destroy.restype = None
+        L.nsfsh_error.argtypes = [vp]
+        L.nsfsh_error.restype = C.c_char_p
+        L.nsfsh_set_map.argtypes = [vp, vp, vp]
+        L.nsfsh_generate_path_idx.argtypes = [vp, i32, i32, i32, i32, vp, i32, C.POINTER(i32)]
+        L.nsfsh_generate_path_pos.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32, C.POINTER(i32)]
+        L.nsfsh_find_better_point_pos.argtypes = [vp, dbl, dbl, C.POINTER(dbl), C.POINTER(dbl)]
+        L.nsfsh_find_better_point_idx.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
+        L.nsfsh_load_config.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]
+        L.nsfsh_main_planner_kind.argtypes = [vp]
+        L.nsfsh_sparsify.argtypes = [vp, i32, vp, i32]
+        _libs[path] = L
+    return _libs[path]
+
+
+def load_config(yaml_path, dropin=False):
+    L = lib(dropin)
+    a, b, c = C.create_string_buffer(32), C.create_string_buffer(32), C.create_string_buffer(32)
+    rate, verbose, device = C.c_double(0), C.c_int(0), C.c_int(0)
+    rc = L.nsfsh_load_config(str(yaml_path).encode(), a, b, c, C.byref(rate), C.byref(verbose), C.byref(device))
+    if rc != 0:
+        raise RuntimeError(f"cannot read {yaml_path}")
+    return dict(planner_name=a.value.decode(), cost_mode=b.value.decode(), djikstra_backend=c.value.decode(),
+                gp_rate=rate.value, verbose_planner=bool(verbose.value), device=device.value)
+
+
+def sparsify(xy, dropin=False):
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    out = np.zeros_like(xy)
+    n = lib(dropin).nsfsh_sparsify(xy.ctypes.data_as(C.c_void_p), len(xy), out.ctypes.data_as(C.c_void_p), len(xy))
+    return out[:n].copy()
+
+
+class PlannerError(RuntimeError):
+    pass
+
+
+class Session:
+    """main_planner_ + fallback_planner_ over one MapData, as GlobalPlanner::setupPlanner builds them."""
+
+    def __init__(self, planner_name, cost_mode, infl, lo, lo_thresh=10, cell=0.05, origin=(0.0, 0.0), backend="exact",
+                 device=0, dropin=False):
+        self.L = lib(dropin)
+        infl = np.ascontiguousarray(infl, np.int32)
+        lo = np.ascontiguousarray(lo, np.int32)
+        self.H, self.W = infl.shape
+        rc = C.c_int(0)
+        self.s = self.L.nsfsh_create(planner_name.encode(), cost_mode.encode(), backend.encode(), self.H, self.W, cell,
+                                     origin[0], origin[1], lo_thresh, infl.ctypes.data_as(C.c_void_p),
+                                     lo.ctypes.data_as(C.c_void_p), device, C.byref(rc))
+        if rc.value != 0:
+            msg = self.L.nsfsh_error(self.s).decode()
+            self.close()
+            raise PlannerError(msg)
+
+    def close(self):
+        if getattr(self, "s", None):
+            self.L.nsfsh_destroy(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def kind(self):
+        return ("astar", "djikstra", "thetastar")[self.L.nsfsh_main_planner_kind(self.s)]
+
+    def set_map(self, infl, lo):
+        infl = np.ascontiguousarray(infl, np.int32)
+        lo = np.ascontiguousarray(lo, np.int32)
+        self.L.nsfsh_set_map(self.s, infl.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p))
+
+    def _path(self, fn, *args):
+        cap = 4 * (self.H + self.W) + 64
+        while True:
+            out = np.zeros((cap, 2), np.float64)
+            n = C.c_int(0)
+            rc = fn(self.s, *args, out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+            if rc == 1:
+                return dict(status="out_of_range", path=None)
+            if rc != 0:
+                raise PlannerError(self.L.nsfsh_error(self.s).decode())
+            if n.value <= cap:
+                return dict(status="ok", path=out[: n.value].copy())
+            cap = n.value
+
+    def generate_path_idx(self, start, goal):
+        return self._path(self.L.nsfsh_generate_path_idx, int(start[0]), int(start[1]), int(goal[0]), int(goal[1]))
+
+    def generate_path_pos(self, start_xy, goal_xy):
+        return self._path(self.L.nsfsh_generate_path_pos, float(start_xy[0]), float(start_xy[1]), float(goal_xy[0]), float(goal_xy[1]))
+
+    def find_better_point(self, bad, as_pos=False):
+        fx, fy = C.c_double(0), C.c_double(0)
+        if as_pos:
+            rc = self.L.nsfsh_find_better_point_pos(self.s, float(bad[0]), float(bad[1]), C.byref(fx), C.byref(fy))
+        else:
+            rc = self.L.nsfsh_find_better_point_idx(self.s, int(bad[0]), int(bad[1]), C.byref(fx), C.byref(fy))
+        if rc == 1:
+            return dict(status="out_of_range", pos=None)
+        if rc != 0:
+            raise PlannerError(self.L.nsfsh_error(self.s).decode())
+        return dict(status="ok", pos=(fx.value, fy.value))

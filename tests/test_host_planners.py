@@ -1,0 +1,147 @@
+"""The C++17 GridPlannerCore children (host/gpu_planners.cpp): interface, runtime selection, and - on the GPU -
+generatePath() / find_better_point() against the golden vectors produced by the reference's own classes.
+
+generatePath = plan + post_process_path (grid_planner_core.cpp:603-615); the golden ``finals`` are the reference's
+world-coordinate outputs, so equality of doubles (``==``) is the bar: the index<->world conversions and the
+collinearity filter are the same fp64 expressions, and the search underneath is order-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import COMBOS, GOLDEN_MAPS, PKG, ROOT, golden_map, split_by
+
+
+@pytest.fixture(scope="module")
+def host_mod():
+    from nsfs import host
+    host.lib()
+    return host
+
+
+def test_host_library_exports_the_shim(host_mod):
+    L = host_mod.lib()
+    for sym in host_mod.SYMBOLS:
+        assert hasattr(L, sym), sym
+
+
+def test_shipped_yaml_selects_like_the_reference(host_mod, tmp_path):
+    cfg = host_mod.load_config(os.path.join(PKG, "global_planner.yaml"))
+    assert cfg["planner_name"] == "astar" and cfg["cost_mode"] == "f" and cfg["gp_rate"] == 25.0 and cfg["verbose_planner"]
+    # defaults of loadParams (global_planner.cpp:482-490) when the keys are absent: astar / fg
+    p = tmp_path / "empty.yaml"
+    p.write_text("com_rate: 25 #rate of commander\n")
+    cfg = host_mod.load_config(p)
+    assert cfg["planner_name"] == "astar" and cfg["cost_mode"] == "fg"
+    # the upstream file's own formatting: quoted values with trailing comments (core_turtle_config.yaml:33-36)
+    p = tmp_path / "core.yaml"
+    p.write_text('gp_rate: 12.5 #rate\nverbose_planner: false #verbosity of logs\nplanner_name: "djikstra" #name of planner --> Options:\n'
+                 'cost_mode: "g" #cost function to use\ndjikstra_backend: field\ngpu_device: 3\n')
+    cfg = host_mod.load_config(p)
+    assert cfg == dict(planner_name="djikstra", cost_mode="g", djikstra_backend="field", gp_rate=12.5, verbose_planner=False, device=3)
+
+
+def test_sparsify_matches_the_oracle_restatement(host_mod, oracle_mod, golden):
+    """sparsifyPath is host arithmetic (no device): run it on every golden raw path."""
+    for mname in GOLDEN_MAPS:
+        O = oracle_mod.Oracle(*golden_map(golden, mname))
+        key = f"{mname}/astar_f"
+        for path in split_by(golden[key + "/paths"], golden[key + "/path_len"]):
+            xy = np.array([O.idx2pos(c) for c in path], np.float64)
+            assert np.array_equal(host_mod.sparsify(xy), O.sparsify(xy))
+
+
+def test_reference_header_build_exists_where_the_reference_is(host_mod):
+    if not os.path.isdir("/root/reference/src/global_planner"):
+        pytest.skip("no /root/reference on this machine")
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    L = host_mod.lib(dropin=True)          # children compiled against the reference's own grid_planner_core.h
+    for sym in host_mod.SYMBOLS:
+        assert hasattr(L, sym), sym
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------
+def _variants(host_mod):
+    v = [False]
+    if os.path.exists(host_mod.DROPIN_SO):
+        v.append(True)
+    return v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mname", GOLDEN_MAPS)
+@pytest.mark.parametrize("combo", COMBOS, ids=lambda c: f"{c[0]}_{c[2]}")
+def test_generate_path_matches_reference_finals(host_mod, golden, mname, combo):
+    aname, _, mode = combo
+    infl, lo = golden_map(golden, mname)
+    key = f"{mname}/{aname}_{mode}"
+    qs = golden[f"{mname}/queries"]
+    finals = split_by(golden[key + "/finals"], golden[key + "/final_len"])
+    for dropin in _variants(host_mod):
+        S = host_mod.Session(aname, mode, infl, lo, dropin=dropin)
+        assert S.kind() == aname
+        for qi, q in enumerate(qs):
+            r = S.generate_path_idx(q[:2], q[2:])
+            if golden[key + "/status"][qi] != 0:
+                assert r["status"] == "out_of_range", (mname, combo, qi)       # std::out_of_range, like vector::at
+                continue
+            assert r["status"] == "ok"
+            assert np.array_equal(r["path"], finals[qi]), (mname, combo, qi, dropin)
+            # the Pos2D overload converts with pos2idx first (grid_planner_core.cpp:610-615)
+            r2 = S.generate_path_pos(np.array(q[:2]) * 0.05 + 0.01, np.array(q[2:]) * 0.05 - 0.01)
+            assert r2["status"] == "ok" and np.array_equal(r2["path"], finals[qi])
+        S.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mname", GOLDEN_MAPS)
+def test_fallback_planner_matches_reference(host_mod, golden, mname):
+    infl, lo = golden_map(golden, mname)
+    for dropin in _variants(host_mod):
+        S = host_mod.Session("astar", "f", infl, lo, dropin=dropin)
+        for b, st, out in zip(golden[f"{mname}/fb_in"], golden[f"{mname}/fb_status"], golden[f"{mname}/fb_out"]):
+            r = S.find_better_point(b)
+            if st != 0:
+                assert r["status"] == "out_of_range"
+                continue
+            assert r["pos"] == (out[0] * 0.05 + 0.0, out[1] * 0.05 + 0.0)     # idx2pos, grid_planner_core.cpp:416-421
+            assert S.find_better_point((b[0] * 0.05, b[1] * 0.05), as_pos=True)["pos"] == r["pos"]
+        S.close()
+
+
+@pytest.mark.gpu
+def test_selection_rule_and_field_backend(host_mod, golden, oracle_mod):
+    infl, lo = golden_map(golden, "m0")
+    S = host_mod.Session("no-such-planner", "zz", infl, lo)          # unknown name => astar, unknown mode => fg
+    assert S.kind() == "astar"
+    O = oracle_mod.Oracle(infl, lo)
+    q = golden["m0/queries"][0]
+    assert np.array_equal(S.generate_path_idx(q[:2], q[2:])["path"], O.generate_path(0, "fg", q[:2], q[2:])["final_xy"])
+    S.close()
+    assert host_mod.Session("thetastar", "f", infl, lo).kind() == "thetastar"
+    # djikstra with the bulk field backend: same reachability and cost as the exact-order search
+    F = host_mod.Session("djikstra", "g", infl, lo, backend="field")
+    E = host_mod.Session("djikstra", "g", infl, lo, backend="exact")
+    for q in golden["m0/queries"][:8]:
+        pf, pe = F.generate_path_idx(q[:2], q[2:])["path"], E.generate_path_idx(q[:2], q[2:])["path"]
+        assert (len(pf) == 1) == (len(pe) == 1)
+        assert np.array_equal(pf[0], pe[0]) and np.array_equal(pf[-1], pe[-1])
+    F.close(); E.close()
+
+
+@pytest.mark.gpu
+def test_map_replaced_between_calls_like_the_ros_callbacks(host_mod, golden, oracle_mod):
+    """global_planner.cpp:65-73 swaps the grid vectors whenever a message arrives; the next plan must see them."""
+    infl, lo = golden_map(golden, "m0")
+    infl2, lo2 = golden_map(golden, "m2")
+    S = host_mod.Session("astar", "f", infl, lo)
+    q = golden["m0/queries"][1]
+    a = S.generate_path_idx(q[:2], q[2:])["path"]
+    assert np.array_equal(a, oracle_mod.Oracle(infl, lo).generate_path(0, "f", q[:2], q[2:])["final_xy"])
+    lo_b = lo.copy()
+    lo_b[q[2], q[3]] = 20                                             # the goal cell becomes occupied
+    S.set_map(infl, lo_b)
+    b = S.generate_path_idx(q[:2], q[2:])["path"]
+    assert np.array_equal(b, oracle_mod.Oracle(infl, lo_b).generate_path(0, "f", q[:2], q[2:])["final_xy"])
+    S.close()
