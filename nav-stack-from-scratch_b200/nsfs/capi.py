@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GPU_SO = os.path.join(PKG, "libnsfs_gpu.so")
+GPU_SO = os.environ.get("NSFS_GPU_SO") or os.path.join(PKG, "libnsfs_gpu.so")   # override: instrumented dev builds only
 
 OK, E_RANGE, E_CUDA, E_TRUNC, E_ARG, E_NOMEM, E_HEAP, E_NOMAP, E_NOFIELD = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ASTAR, DJIKSTRA, THETASTAR, DJIKSTRA_FIELD = 0, 1, 2, 3
