@@ -116,6 +116,22 @@ int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_
  * cost = (#cardinal-cost steps) + (#diagonal-cost steps) * sqrt(2) in double. */
 int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n_path, double* cost);
 
+/* ---- row-partitioned field (one shard of a map split by row blocks across GPUs) ---------------
+ * The shard's handle covers its owned rows plus 4 rows of map on either side (2 ghost rows whose g is exchanged
+ * + 2 more so the ghost rows' edge masks see their true neighbourhood).  Before nsfs_set_map*, restrict
+ * propagation with nsfs_set_option("active_row_lo"/"active_row_hi") and the counters with "count_row_lo"/"count_row_hi"
+ * (local row numbers, hi exclusive, 0 = unset).  Then per solve:
+ *   nsfs_field_begin(h, si, sj)            g = 1e5 everywhere; (si, sj) local source, or si < 0 when another shard owns it
+ *   repeat { nsfs_field_inject_rows(..)    g[row0 .. row0+nrows) = min(g, vals): ghost rows received from a neighbour shard
+ *            nsfs_field_relax(h, st) }     relax to the local fixed point; the caller exchanges boundary rows between shards
+ *   nsfs_field_finish(h, st)               predecessor field + reached count of the counted rows; then nsfs_field_device*
+ * All three leave results on the device (nsfs_field_device's pointers stay valid). */
+int nsfs_field_begin(nsfs_t* h, int si, int sj);
+int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, int* n_improved);   /* device values */
+int nsfs_field_relax(nsfs_t* h, nsfs_stats* st);
+int nsfs_field_finish(nsfs_t* h, nsfs_stats* st);
+int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred);   /* valid after nsfs_field_begin */
+
 /* ---- fallback ------------------------------------------------------------------------------------
  * replaces: Djikstra::find_better_point(Index, MapData&) (djikstra.cpp:165-273) on a planner prepared
  * with cost mode "g" (global_planner.cpp:127-128).  (fi, fj) = first popped free cell, or the input cell

@@ -54,6 +54,7 @@ static int finish_map(nsfs_planner* h) {
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_map = true;
     h->field.valid = false;
+    h->field.begun = false;
     return NSFS_OK;
 }
 
@@ -253,6 +254,7 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     return NSFS_OK;
 }
 
+static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches0, float ms, float main_ms);
 int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_t** d_pred, nsfs_stats* st);
 int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n_path, double* cost);
 
@@ -354,19 +356,88 @@ int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_
     if (rc != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
+    h->field.begun = true;
+    if (d_g) *d_g = h->field.g;
+    if (d_pred) *d_pred = h->field.pred;
+    if ((rc = field_read_counts(h, st, launches0, ms, tm.main_kernel_ms())) != NSFS_OK) return rc;
+    h->field.valid = true;
+    return NSFS_OK;
+}
+
+// ---- row-partitioned field: the same solve in caller-driven phases ----------------------------------------
+int nsfs_field_begin(nsfs_t* h, int si, int sj) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (si >= 0 && (si >= h->H || sj < 0 || sj >= h->W)) return NSFS_E_ARG;
+    if ((rc = launch_field_begin(h, si, sj)) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->field.begun = true;
+    return NSFS_OK;
+}
+
+int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, int* n_improved) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    if (row0 < 0 || nrows < 0 || row0 + nrows > h->H || (nrows && !d_vals)) return NSFS_E_ARG;
+    if ((rc = ensure_scratch(h, 256)) != NSFS_OK) return rc;
+    int* d_cnt = (int*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
+    h->field.valid = false;
+    if ((rc = launch_field_inject(h, row0, nrows, d_vals, d_cnt)) != NSFS_OK) return rc;
+    int cnt = 0;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n_improved) *n_improved = cnt;
+    return NSFS_OK;
+}
+
+static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches0, float ms, float main_ms) {
     int counts[8];
     NSFS_CUDA_TRY(h, cudaMemcpyAsync(counts, h->field.counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (st) {
         memset(st, 0, sizeof(*st));
         st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5]; st->pops = counts[6];
-        st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = tm.main_kernel_ms();
+        st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
     }
-    if (d_g) *d_g = h->field.g;
-    if (d_pred) *d_pred = h->field.pred;
     if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }
     if (counts[4] & 1) return NSFS_E_RANGE; // a reached cell's expansion throws in the reference
-    h->field.valid = true;
+    return NSFS_OK;
+}
+
+int nsfs_field_relax(nsfs_t* h, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    const long long launches0 = h->launches;
+    Timer tm(h);
+    if ((rc = launch_field_relax(h)) != NSFS_OK) return rc;
+    const float ms = tm.stop_sync();
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return field_read_counts(h, st, launches0, ms, tm.main_kernel_ms());
+}
+
+int nsfs_field_finish(nsfs_t* h, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    const long long launches0 = h->launches;
+    Timer tm(h);
+    if ((rc = launch_field_finish(h)) != NSFS_OK) return rc;
+    const float ms = tm.stop_sync();
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    rc = field_read_counts(h, st, launches0, ms, 0.f);
+    if (rc == NSFS_OK) h->field.valid = true;
+    return rc;
+}
+
+int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    if (d_g) *d_g = h->field.g;
+    if (d_pred) *d_pred = h->field.pred;
     return NSFS_OK;
 }
 
@@ -457,6 +528,10 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_alpha")) { h->opt_field_alpha = value; return NSFS_OK; }
+    if (!strcmp(key, "active_row_lo")) { h->opt_active_row_lo = value; h->have_map = false; return NSFS_OK; }   // masks depend on it: set the map again
+    if (!strcmp(key, "active_row_hi")) { h->opt_active_row_hi = value; h->have_map = false; return NSFS_OK; }
+    if (!strcmp(key, "count_row_lo")) { h->opt_count_row_lo = value; return NSFS_OK; }
+    if (!strcmp(key, "count_row_hi")) { h->opt_count_row_hi = value; return NSFS_OK; }
     return NSFS_E_ARG;
 }
 

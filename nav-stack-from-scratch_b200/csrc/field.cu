@@ -74,6 +74,11 @@ __global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* 
 __global__ void field_seed_kernel(FieldParams p, const uint32_t* __restrict__ free_bits,
                                   const uint16_t* __restrict__ out_mask, int si, int sj) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (si < 0) {                               // no source on this shard: everything arrives through field_inject_kernel
+        for (int c = 0; c < 8; ++c) p.counts[c] = 0;
+        p.counts[7] = __float_as_int(-1e30f);
+        return;
+    }
     const long long ks = (long long)si * p.W + sj;
     p.g[ks] = 0.0f;
     auto tile_of = [&](long long k) { return (int)(k / p.W) / TS * p.tiles_x + (int)(k % p.W) / TS; };
@@ -93,6 +98,27 @@ __global__ void field_seed_kernel(FieldParams p, const uint32_t* __restrict__ fr
     for (int c = 0; c < 8; ++c) p.counts[c] = 0;
     p.counts[1] = pend;                        // asynchronous scheduler: pending tiles + visits in flight
     p.counts[7] = __float_as_int(-1e30f);      // previous round's threshold
+}
+
+// Row injection for the row-partitioned multi-GPU field: g[row0*W + t] = min(g, vals[t]) over whole rows.
+// An improved cell makes its tile pending with that value as key, exactly like a halo post from a neighbouring tile.
+__global__ void __launch_bounds__(256) field_inject_kernel(FieldParams p, long long k0, long long n, const float* __restrict__ vals,
+                                                           int* __restrict__ improved) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool better = false;
+    if (t < n) {
+        const long long k = k0 + t;
+        const float v = vals[t], old = p.g[k];
+        if (v < old) {
+            p.g[k] = v;
+            better = true;
+            const int tile = (int)(k / p.W) / TS * p.tiles_x + (int)(k % p.W) / TS;
+            const uint32_t was = atomicMin(p.tile_key + tile, __float_as_uint(v));
+            if (was == kNoKey) atomicAdd(p.counts + 1, 1);
+        }
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, better);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(improved, __popc(b));
 }
 
 // Relax one tile to its local fixed point (under the band limit thr).
@@ -434,6 +460,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) field_solve_async_kernel(Fie
 // of them is a valid optimal predecessor (north_star: path validity exact, cost within 1e-5).
 __global__ void __launch_bounds__(256) field_pred_kernel(const float* __restrict__ g, const uint16_t* __restrict__ in_mask,
                                                          const uint16_t* __restrict__ out_mask, int W, long long N, long long ks,
+                                                         long long count_lo, long long count_hi,
                                                          uint8_t* __restrict__ pred, int* __restrict__ counts) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int reached = 0, thrown = 0;
@@ -441,8 +468,9 @@ __global__ void __launch_bounds__(256) field_pred_kernel(const float* __restrict
         const float gv = g[v];
         uint8_t pd = 255;
         if (gv < kInfF) {
-            reached = 1;
-            if (__ldg(out_mask + v) & kThrowBit) thrown = 1;   // a reached cell is expanded; expanding this one throws
+            const bool counted = v >= count_lo && v < count_hi;     // a row-partitioned shard counts its own rows only
+            reached = counted;
+            if (counted && (__ldg(out_mask + v) & kThrowBit)) thrown = 1;   // a reached cell is expanded; expanding this one throws
             if (v != ks) {
                 const uint32_t m = __ldg(in_mask + v);
 #pragma unroll
@@ -513,37 +541,60 @@ void field_free(nsfs_planner* h) {
     f = FieldWork();
 }
 
-int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
-    int rc = field_alloc(h);
-    if (rc != NSFS_OK) return rc;
+static FieldParams field_params(nsfs_planner* h) {
     FieldWork& f = h->field;
-    f.valid = false;
     FieldParams p;
     p.g = f.g; p.in_mask = h->d_in_mask; p.tile_key = f.tile_key; p.list = f.list[0];
     p.counts = f.counts; p.H = h->H; p.W = h->W; p.N = h->N; p.tiles_x = f.tiles_x; p.tiles_y = f.tiles_y;
     p.max_rounds = 1 << 30;
     p.prof = nullptr;
+    p.inner = h->opt_field_inner > 0 ? (int)h->opt_field_inner : 8;
+    p.idle_ns = h->opt_field_idle_ns > 0 ? (unsigned)h->opt_field_idle_ns : 1000u;
+    p.delta = h->opt_field_delta > 0 ? (float)h->opt_field_delta : 128.0f;
+    p.alpha = h->opt_field_alpha >= 0 ? (float)h->opt_field_alpha / 100.0f : 0.5f;
+    return p;
+}
+
+// Phase 1: g = 1e5 everywhere, no pending tile; (si, sj) is the source or si < 0 for "no source on this shard".
+int launch_field_begin(nsfs_planner* h, int si, int sj) {
+    int rc = field_alloc(h);
+    if (rc != NSFS_OK) return rc;
+    FieldWork& f = h->field;
+    f.valid = false;
+    FieldParams p = field_params(h);
+    const long long n4 = h->N / 4;
+    long long fill_blocks = (n4 + 255) / 256;
+    if (fill_blocks < 1) fill_blocks = 1;
+    if (fill_blocks > (long long)h->sm_count * 8) fill_blocks = (long long)h->sm_count * 8;
+    field_fill_kernel<<<(int)fill_blocks, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, h->N, f.tile_key, f.tiles_x * f.tiles_y);
+    field_seed_kernel<<<1, 32, 0, h->stream>>>(p, h->d_free, h->d_out_mask, si, sj);
+    h->launches += 2;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    f.src_i = si; f.src_j = sj;
+    return NSFS_OK;
+}
+
+// Phase 2 (optional, repeatable): lower whole rows of g from device values; d_improved accumulates the cells lowered.
+int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved) {
+    FieldParams p = field_params(h);
+    const long long n = (long long)nrows * h->W;
+    if (n <= 0) return NSFS_OK;
+    field_inject_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(p, (long long)row0 * h->W, n, d_vals, d_improved);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+// Phase 3 (repeatable): relax every pending tile until nothing is pending.
+int launch_field_relax(nsfs_planner* h) {
+    FieldWork& f = h->field;
+    FieldParams p = field_params(h);
 #if NSFS_FIELD_PROF
     static unsigned long long* d_prof = nullptr;
     if (!d_prof) cudaMalloc(&d_prof, 8 * 4100);
     cudaMemsetAsync(d_prof, 0, 8 * 4100, h->stream);
     p.prof = d_prof;
 #endif
-    p.inner = h->opt_field_inner > 0 ? (int)h->opt_field_inner : 8;
-    p.idle_ns = h->opt_field_idle_ns > 0 ? (unsigned)h->opt_field_idle_ns : 1000u;
-    p.delta = h->opt_field_delta > 0 ? (float)h->opt_field_delta : 128.0f;
-    p.alpha = h->opt_field_alpha >= 0 ? (float)h->opt_field_alpha / 100.0f : 0.5f;
-
-    const long long n4 = h->N / 4;
-    long long fill_blocks = (n4 + 255) / 256;
-    if (fill_blocks < 1) fill_blocks = 1;
-    if (fill_blocks > (long long)h->sm_count * 8) fill_blocks = (long long)h->sm_count * 8;
-    const int fill_grid = (int)fill_blocks;
-    field_fill_kernel<<<fill_grid, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, h->N, f.tile_key, f.tiles_x * f.tiles_y);
-    field_seed_kernel<<<1, 32, 0, h->stream>>>(p, h->d_free, h->d_out_mask, si, sj);
-    h->launches += 2;
-    NSFS_CUDA_TRY(h, cudaGetLastError());
-
     int per_sm = 0;
     const bool async_tiles = h->opt_field_mode != 1;
     NSFS_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, async_tiles ? field_solve_async_kernel : field_solve_kernel, FIELD_THREADS, 0));
@@ -557,12 +608,7 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
     NSFS_CUDA_TRY(h, cudaLaunchCooperativeKernel(async_tiles ? (void*)field_solve_async_kernel : (void*)field_solve_kernel, dim3(grid),
                                                  dim3(FIELD_THREADS), args, 0, h->stream));
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
-    const long long ks = (long long)si * h->W + sj;
-    field_pred_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f.g, h->d_in_mask, h->d_out_mask, h->W, h->N, ks,
-                                                                             f.pred, f.counts);
-    h->launches += 2;
-    NSFS_CUDA_TRY(h, cudaGetLastError());
-    f.src_i = si; f.src_j = sj;
+    h->launches++;
 #if NSFS_FIELD_PROF
     { static unsigned long long hp[4100]; cudaMemcpyAsync(hp, p.prof, 8 * 4100, cudaMemcpyDeviceToHost, h->stream); cudaStreamSynchronize(h->stream);
       unsigned long long summax = 0; int nr = 0; for (int r = 0; r < 4000; ++r) { summax += hp[16 + r]; if (hp[16 + r]) nr = r + 1; }
@@ -571,8 +617,28 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
       fprintf(stderr, "[field prof] grid %d: per-block avg cycles: kernel %.0f relax %.0f | tile sums: load %.0f sweeps %.0f tail %.0f (cycles, summed over visits) | sub-block iterations %llu\n",
               grid, (double)hp[4] / grid, (double)hp[5] / grid, (double)hp[0], (double)hp[1], (double)hp[2], hp[3]); }
 #endif
-    (void)st;
     return NSFS_OK;
+}
+
+// Phase 4: predecessor field, reached count and "would throw" flag over the rows [count_row_lo, count_row_hi).
+int launch_field_finish(nsfs_planner* h) {
+    FieldWork& f = h->field;
+    const long long ks = f.src_i >= 0 ? (long long)f.src_i * h->W + f.src_j : -1;
+    const long long lo = (long long)(h->opt_count_row_lo > 0 ? h->opt_count_row_lo : 0) * h->W;
+    const long long hi = h->opt_count_row_hi > 0 ? (long long)h->opt_count_row_hi * h->W : h->N;
+    field_pred_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f.g, h->d_in_mask, h->d_out_mask, h->W, h->N, ks, lo, hi,
+                                                                             f.pred, f.counts);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
+    (void)st;
+    int rc = launch_field_begin(h, si, sj);
+    if (rc == NSFS_OK) rc = launch_field_relax(h);
+    if (rc == NSFS_OK) rc = launch_field_finish(h);
+    return rc;
 }
 
 int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap, int* d_n, double* d_cost, int* d_status) {

@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restric
 // ---- kernel 3: in-edge masks (pull form used by the field relaxation) --------------------------------
 __global__ void __launch_bounds__(256) in_mask_kernel(const uint32_t* __restrict__ free_bits,
                                                       const uint16_t* __restrict__ out_mask, int H, int W, long long N,
-                                                      uint16_t* __restrict__ in_mask) {
+                                                      long long active_lo, long long active_hi, uint16_t* __restrict__ in_mask) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
     uint32_t m = 0;
-    if (bit_at(free_bits, v)) {
+    if (bit_at(free_bits, v) && v >= active_lo && v < active_hi) {    // rows outside the window take no in-edges (shards)
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
             const long long u = v - nb_off(d, W);
@@ -124,7 +124,9 @@ int launch_build_masks(nsfs_planner* h) {
     const int block = 256;
     const long long grid = (h->N + block - 1) / block;
     out_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, h->d_out_mask);
-    in_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, h->d_in_mask);
+    const long long a_lo = (h->opt_active_row_lo > 0 ? h->opt_active_row_lo : 0) * (long long)h->W;
+    const long long a_hi = h->opt_active_row_hi > 0 ? h->opt_active_row_hi * (long long)h->W : h->N;
+    in_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, a_lo, a_hi, h->d_in_mask);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;

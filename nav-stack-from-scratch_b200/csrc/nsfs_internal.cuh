@@ -40,7 +40,8 @@ struct FieldWork {
     int*      counts = nullptr;    // [8]: 0/1 list lengths, 2 rounds, 3 tile visits, 4 error flag, 5 reached
     int       tiles_x = 0, tiles_y = 0;
     int       src_i = -1, src_j = -1;
-    bool      valid = false;
+    bool      valid = false;       // solved and finished: nsfs_field_path may walk pred
+    bool      begun = false;       // g holds a field in progress (nsfs_field_begin or a full solve ran)
 };
 
 struct SearchWork {
@@ -89,6 +90,10 @@ struct nsfs_planner {
     long long opt_field_mode = 0;       // 0 = asynchronous tile scheduling, 1 = bulk-synchronous rounds
     long long opt_field_idle_ns = 0;    // 0 = default (100)
     long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    // row-partitioned shards: rows outside [active_row_lo, active_row_hi) take no in-edges (they only exist
+    // so the masks of the rows next to them see the right neighbourhood); counts cover [count_row_lo, count_row_hi)
+    long long opt_active_row_lo = 0, opt_active_row_hi = 0;   // hi == 0: all rows
+    long long opt_count_row_lo = 0, opt_count_row_hi = 0;
     char cuda_error[256] = {0};
 };
 
@@ -102,6 +107,10 @@ int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out);
 int field_alloc(nsfs_planner* h);
 void field_free(nsfs_planner* h);
 int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
+int launch_field_begin(nsfs_planner* h, int si, int sj);
+int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved);
+int launch_field_relax(nsfs_planner* h);
+int launch_field_finish(nsfs_planner* h);
 int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap, int* d_n, double* d_cost, int* d_status);
 
 int search_alloc(nsfs_planner* h, int want_slots);

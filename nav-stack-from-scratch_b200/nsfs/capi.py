@@ -61,6 +61,11 @@ def lib():
         L.nsfs_plan_batch_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_field.argtypes = [vp, i32, i32, vp, vp, C.POINTER(Stats)]
         L.nsfs_field_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
+        L.nsfs_field_begin.argtypes = [vp, i32, i32]
+        L.nsfs_field_inject_rows.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
+        L.nsfs_field_relax.argtypes = [vp, C.POINTER(Stats)]
+        L.nsfs_field_finish.argtypes = [vp, C.POINTER(Stats)]
+        L.nsfs_field_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.nsfs_field_path.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(dbl)]
         L.nsfs_find_better_point.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(Stats)]
         L.nsfs_find_better_point_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(Stats)]
@@ -191,6 +196,33 @@ class Planner:
         rc = self.L.nsfs_field_device(self.h, int(start[0]), int(start[1]), C.byref(dg), C.byref(dp), C.byref(st))
         self._check(rc, allow=(E_RANGE,))
         return dict(status=rc, d_g=dg.value, d_pred=dp.value, reached=st.expansions, stats=st.asdict())
+
+    # -- row-partitioned field: caller-driven phases (nsfs/sharded_field.py) -----------------------
+    def field_begin(self, start=None):
+        si, sj = (-1, -1) if start is None else (int(start[0]), int(start[1]))
+        self._check(self.L.nsfs_field_begin(self.h, si, sj))
+
+    def field_inject_rows(self, row0, nrows, d_vals_ptr):
+        n = C.c_int(0)
+        self._check(self.L.nsfs_field_inject_rows(self.h, int(row0), int(nrows), C.c_void_p(d_vals_ptr), C.byref(n)))
+        return n.value
+
+    def field_relax(self):
+        st = Stats()
+        rc = self.L.nsfs_field_relax(self.h, C.byref(st))
+        self._check(rc, allow=(E_RANGE,))
+        return dict(status=rc, stats=st.asdict())
+
+    def field_finish(self):
+        st = Stats()
+        rc = self.L.nsfs_field_finish(self.h, C.byref(st))
+        self._check(rc, allow=(E_RANGE,))
+        return dict(status=rc, reached=st.expansions, stats=st.asdict())
+
+    def field_pointers(self):
+        dg, dp = C.c_void_p(), C.c_void_p()
+        self._check(self.L.nsfs_field_pointers(self.h, C.byref(dg), C.byref(dp)))
+        return dg.value, dp.value
 
     def field_path(self, goal, cap=None):
         cap = int(cap if cap is not None else self.N + 1)

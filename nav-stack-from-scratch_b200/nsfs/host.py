@@ -1,10 +1,10 @@
 """ctypes front-end of the C++ planner children (host/gpu_planners.cpp) through their nsfsh_* test shim.
 
 ``Session`` is what GlobalPlanner holds (reference global_planner.h:52-53): a main planner picked by
-planner_name / cost_mode and a Djikstra fallback prepared with cost mode "g".  Two builds expose the same shim:
-  libnsfs_planners.so            the in-repo build against the interface mirror (host/planner_iface.hpp)
-  oracle/_ref/libnsfs_dropin.so  the same children compiled against the reference's OWN grid_planner_core.h
-                                 (built only where /root/reference exists; pass dropin=True)
+planner_name / cost_mode and a Djikstra fallback prepared with cost mode "g".  The default library is
+libnsfs_planners.so, the in-repo build against the interface mirror (host/planner_iface.hpp); ``so_path`` selects
+another build of the same children, e.g. the one the tests compile against the reference's OWN grid_planner_core.h
+where the reference tree exists.
 """
 from __future__ import annotations
 
@@ -16,7 +16,6 @@ import numpy as np
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ROOT = os.path.dirname(PKG)
 HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
-DROPIN_SO = os.path.join(ROOT, "oracle", "_ref", "libnsfs_dropin.so")
 
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
@@ -25,8 +24,8 @@ SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsf
 _libs = {}
 
 
-def lib(dropin=False):
-    path = DROPIN_SO if dropin else HOST_SO
+def lib(so_path=None):
+    path = so_path or HOST_SO
     if path not in _libs:
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} not built")
@@ -50,8 +49,8 @@ def lib(dropin=False):
     return _libs[path]
 
 
-def load_config(yaml_path, dropin=False):
-    L = lib(dropin)
+def load_config(yaml_path, so_path=None):
+    L = lib(so_path)
     a, b, c = C.create_string_buffer(32), C.create_string_buffer(32), C.create_string_buffer(32)
     rate, verbose, device = C.c_double(0), C.c_int(0), C.c_int(0)
     rc = L.nsfsh_load_config(str(yaml_path).encode(), a, b, c, C.byref(rate), C.byref(verbose), C.byref(device))
@@ -61,10 +60,10 @@ def load_config(yaml_path, dropin=False):
                 gp_rate=rate.value, verbose_planner=bool(verbose.value), device=device.value)
 
 
-def sparsify(xy, dropin=False):
+def sparsify(xy, so_path=None):
     xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
     out = np.zeros_like(xy)
-    n = lib(dropin).nsfsh_sparsify(xy.ctypes.data_as(C.c_void_p), len(xy), out.ctypes.data_as(C.c_void_p), len(xy))
+    n = lib(so_path).nsfsh_sparsify(xy.ctypes.data_as(C.c_void_p), len(xy), out.ctypes.data_as(C.c_void_p), len(xy))
     return out[:n].copy()
 
 
@@ -76,8 +75,8 @@ class Session:
     """main_planner_ + fallback_planner_ over one MapData, as GlobalPlanner::setupPlanner builds them."""
 
     def __init__(self, planner_name, cost_mode, infl, lo, lo_thresh=10, cell=0.05, origin=(0.0, 0.0), backend="exact",
-                 device=0, dropin=False):
-        self.L = lib(dropin)
+                 device=0, so_path=None):
+        self.L = lib(so_path)
         infl = np.ascontiguousarray(infl, np.int32)
         lo = np.ascontiguousarray(lo, np.int32)
         self.H, self.W = infl.shape

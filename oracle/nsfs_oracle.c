@@ -485,3 +485,45 @@ out:
     free(fifo); free(inq);
     return status;
 }
+
+/* Warm-started variant of the fixed point above for ONE ROW-BLOCK SHARD of a partitioned map: g is
+ * in/out, every finite cell is a source, and cells outside rows [row_lo, row_hi) take no in-edges (they exist only so
+ * that their neighbours' direction costs see the true neighbourhood).  slack = the relaxation slack (the reference uses
+ * 1e-5, astar.cpp:116; 0 makes the fixed point unique so sharded and monolithic solves can be compared bit for bit).
+ * Returns the number of label improvements, or a negative NSO_E_* code. */
+long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack) {
+    const int H = m->H, W = m->W;
+    const long long N = (long long)H * W;
+    int32_t* fifo = (int32_t*)malloc((size_t)N * sizeof(int32_t));
+    uint8_t* inq = (uint8_t*)calloc((size_t)N, 1);
+    if (!fifo || !inq) { free(fifo); free(inq); return NSO_E_NOMEM; }
+    long long head = 0, cnt = 0, improved = 0;
+    for (long long k = 0; k < N; ++k)
+        if (g[k] < G_INF) { fifo[cnt++] = (int32_t)k; inq[k] = 1; }
+    long long status = 0;
+    while (cnt) {
+        long long ku = fifo[head]; head = (head + 1) % N; cnt--; inq[ku] = 0;
+        int i = (int)(ku / W), j = (int)(ku % W), card = 1;
+        for (int d = 0; d < 8; ++d) {
+            int t = nso_test_pos(m, i + DI[d], j + DJ[d]);
+            if (t == NSO_E_RANGE) {            /* would throw when expanded: only an error if this cell is a counted one */
+                if (i >= row_lo && i < row_hi) { status = NSO_E_RANGE; goto out; }
+                continue;
+            }
+            if (!t) continue;
+            long long kv = ku + (long long)DI[d] * W + DJ[d];
+            int vi = (int)(kv / W);
+            double cand = g[ku] + (card ? 1 : M_SQRT2);
+            card = !card;
+            if (vi < row_lo || vi >= row_hi) continue;
+            if (g[kv] > cand + slack) {
+                g[kv] = cand; improved++;
+                if (!inq[kv]) { fifo[(head + cnt) % N] = (int32_t)kv; cnt++; inq[kv] = 1; }
+            }
+        }
+    }
+out:
+    free(fifo); free(inq);
+    return status < 0 ? status : improved;
+}
+

@@ -1,0 +1,60 @@
+"""Row-partitioned field on the GPU (SURVEY.md §8e / BASELINE C5): several shards of one map, each its own nsfs handle
+over its held rows, solved in lockstep on one device, against the single-handle field.  The fp32 fixed point is unique,
+so the bar is bit-identical g, identical predecessors and reached counts."""
+import numpy as np
+import pytest
+
+from nsfs import mapgen, sharded_field as sf
+
+pytestmark = pytest.mark.gpu
+
+
+def _mono(gpu_lib, infl, lo, src):
+    P = gpu_lib.Planner(*infl.shape)
+    P.set_map(infl, lo)
+    r = P.field(src)
+    P.close()
+    return r
+
+
+@pytest.mark.parametrize("spec", [(700, 520, 0.10, 51, True, 3), (260, 300, 0.22, 52, True, 4), (300, 130, 0.12, 53, False, 2)],
+                         ids=["3-shards", "4-shards-dense", "2-shards-unframed-wrap"])
+def test_sharded_field_is_bit_identical_to_one_handle(gpu_lib, spec):
+    H, W, p, seed, frame, world = spec
+    infl, lo = mapgen.synth_map(H, W, p, seed, False, frame)
+    if not frame:
+        for c in ((0, 0), (1, 0), (H - 1, W - 1), (H - 2, W - 1)):     # keep the wrap, drop the four throwing cells
+            infl[c] = 1
+            lo[c] = 20
+    src = mapgen.sample_free_cells(infl, lo, 1, seed)[0]
+    want = _mono(gpu_lib, infl, lo, src)
+    assert want["status"] == 0
+    part = sf.RowPartition(H, W, world)
+    shards = [sf.make_gpu_shard(part, r, infl, lo) for r in range(world)]
+    out = sf.solve_in_process(shards, src)
+    assert all(r["status"] == 0 for r in out["results"])
+    g = np.concatenate([s.owned_rows().cpu().numpy() for s in shards])
+    pred = np.concatenate([s.solver.pred_rows(s.loc(s.r0), s.r1 - s.r0).cpu().numpy() for s in shards])
+    assert np.array_equal(g, want["g"])
+    assert np.array_equal(pred, want["pred"])
+    assert sum(r["reached"] for r in out["results"]) == want["reached"]
+    assert out["rounds"] >= 2
+    for s in shards:
+        s.solver.close()
+
+
+def test_shard_without_source_and_unreachable_rows(gpu_lib):
+    """A wall across the map: the shards beyond it stay at 1e5 and the loop still terminates."""
+    infl, lo = mapgen.synth_map(200, 160, 0.05, 54)
+    infl[120, :] = 1
+    lo[120, :] = 20
+    src = (30, 80) if mapgen.free_mask(infl, lo)[30, 80] else tuple(mapgen.sample_free_cells(infl[:100], lo[:100], 1, 54)[0])
+    want = _mono(gpu_lib, infl, lo, src)
+    part = sf.RowPartition(200, 160, 4)
+    shards = [sf.make_gpu_shard(part, r, infl, lo) for r in range(4)]
+    out = sf.solve_in_process(shards, src)
+    g = np.concatenate([s.owned_rows().cpu().numpy() for s in shards])
+    assert np.array_equal(g, want["g"]) and (g[121:] >= 1e5).all()
+    assert out["results"][3]["reached"] == 0
+    for s in shards:
+        s.solver.close()

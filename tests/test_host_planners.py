@@ -12,6 +12,10 @@ import pytest
 from conftest import COMBOS, GOLDEN_MAPS, PKG, ROOT, golden_map, split_by
 
 
+# our children compiled against the reference's own headers + base-class sources (oracle/Makefile, reference present only)
+DROPIN_SO = os.path.join(ROOT, "oracle", "_ref", "libnsfs_dropin.so")
+
+
 @pytest.fixture(scope="module")
 def host_mod():
     from nsfs import host
@@ -56,16 +60,16 @@ def test_reference_header_build_exists_where_the_reference_is(host_mod):
         pytest.skip("no /root/reference on this machine")
     import subprocess
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
-    L = host_mod.lib(dropin=True)          # children compiled against the reference's own grid_planner_core.h
+    L = host_mod.lib(DROPIN_SO)          # children compiled against the reference's own grid_planner_core.h
     for sym in host_mod.SYMBOLS:
         assert hasattr(L, sym), sym
 
 
 # ---- GPU ------------------------------------------------------------------------------------------------------
 def _variants(host_mod):
-    v = [False]
-    if os.path.exists(host_mod.DROPIN_SO):
-        v.append(True)
+    v = [None]
+    if os.path.exists(DROPIN_SO):
+        v.append(DROPIN_SO)
     return v
 
 
@@ -78,8 +82,8 @@ def test_generate_path_matches_reference_finals(host_mod, golden, mname, combo):
     key = f"{mname}/{aname}_{mode}"
     qs = golden[f"{mname}/queries"]
     finals = split_by(golden[key + "/finals"], golden[key + "/final_len"])
-    for dropin in _variants(host_mod):
-        S = host_mod.Session(aname, mode, infl, lo, dropin=dropin)
+    for so in _variants(host_mod):
+        S = host_mod.Session(aname, mode, infl, lo, so_path=so)
         assert S.kind() == aname
         for qi, q in enumerate(qs):
             r = S.generate_path_idx(q[:2], q[2:])
@@ -87,7 +91,7 @@ def test_generate_path_matches_reference_finals(host_mod, golden, mname, combo):
                 assert r["status"] == "out_of_range", (mname, combo, qi)       # std::out_of_range, like vector::at
                 continue
             assert r["status"] == "ok"
-            assert np.array_equal(r["path"], finals[qi]), (mname, combo, qi, dropin)
+            assert np.array_equal(r["path"], finals[qi]), (mname, combo, qi, so)
             # the Pos2D overload converts with pos2idx first (grid_planner_core.cpp:610-615)
             r2 = S.generate_path_pos(np.array(q[:2]) * 0.05 + 0.01, np.array(q[2:]) * 0.05 - 0.01)
             assert r2["status"] == "ok" and np.array_equal(r2["path"], finals[qi])
@@ -98,8 +102,8 @@ def test_generate_path_matches_reference_finals(host_mod, golden, mname, combo):
 @pytest.mark.parametrize("mname", GOLDEN_MAPS)
 def test_fallback_planner_matches_reference(host_mod, golden, mname):
     infl, lo = golden_map(golden, mname)
-    for dropin in _variants(host_mod):
-        S = host_mod.Session("astar", "f", infl, lo, dropin=dropin)
+    for so in _variants(host_mod):
+        S = host_mod.Session("astar", "f", infl, lo, so_path=so)
         for b, st, out in zip(golden[f"{mname}/fb_in"], golden[f"{mname}/fb_status"], golden[f"{mname}/fb_out"]):
             r = S.find_better_point(b)
             if st != 0:
