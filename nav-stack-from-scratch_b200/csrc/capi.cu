@@ -232,7 +232,8 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     fill_stats(st, s5, h->launches - launches0, ms, tm.main_kernel_ms());
 
     // ---- open-list overflow: redo those queries one at a time with the worst-case capacity ----------------
-    const long long worst = 8 * h->N + 16;
+    long long worst = 8 * h->N + 16;
+    if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;      // search_alloc clamps to 32-bit heap positions
     for (int q = 0; q < nq; ++q) {
         if (stat_h[q] != NSFS_E_HEAP || h->search.heap_cap >= worst) continue;
         const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots;

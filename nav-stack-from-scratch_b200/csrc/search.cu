@@ -5,9 +5,20 @@
 // re-labelled (astar.cpp:116-121), and ties between equal int keys are broken only by the mechanics of
 // libstdc++'s binary heap.  Matching its paths, costs and fallback cells therefore means replaying its pop
 // order exactly (SURVEY.md "three facts" #3).  Each warp replays one query:
-//   - the open list is a device binary heap that performs std::push_heap / std::pop_heap step for step
-//     (bits/stl_heap.h __push_heap / __adjust_heap: the hole always sinks to a leaf preferring the right child
-//     unless it sorts after the left one, then the displaced last element is sifted up);
+//   - the open list is a device binary heap that ends every push and pop in exactly the array std::push_heap /
+//     std::pop_heap would leave (bits/stl_heap.h __push_heap / __adjust_heap: the hole sinks to a leaf preferring the
+//     right child unless it sorts after the left one, then the displaced last element is sifted back up), but the
+//     WARP walks it, not one thread:
+//       pop   the 31 internal nodes of a 5-level subtree under the hole are examined at once, lane t loading both
+//             children of node t with one 128-bit load; two ballots (which child wins / where the displaced element
+//             stops) give the path through the five levels with register bit operations, so a sift-down costs one
+//             memory round trip per five levels instead of one per level.  Stopping at the first picked child that
+//             sorts after the displaced element is the same final array as "sink to the leaf, then sift up" because
+//             priorities never decrease along a root-to-leaf path;
+//       push  lane L loads the L-th ancestor of the new leaf, one ballot finds how far the element rises, and the
+//             lanes shift that run of ancestors down in parallel: one round trip per push whatever the distance;
+//   - the loads an expansion needs (the popped cell, its edge mask, its 8 neighbours' records) depend only on the key
+//     at the top of the heap, so they are issued BEFORE the sift-down and their latency hides behind it;
 //   - entries are one 64-bit word  f:18 | g:17 | key:29  so a comparator is a shift and a compare;
 //   - the node store (grid_planner_core.h:26-33) is one 16-byte record per cell {g (fp64), parent key,
 //     epoch<<1 | visited}: the fp64 sums are the reference's own sums in the reference's own order, so g is
@@ -33,7 +44,8 @@ struct SearchParams {
     int* work_counter;
     int H, W;
     long long N;
-    long long heap_cap;
+    long long heap_cap;           // entries a query's open list may hold
+    long long heap_stride;        // array positions per slot (heap_cap + slack for position 0 and the pair over-read; even)
     int slots;
     int mode;
     int nq;
@@ -47,59 +59,87 @@ struct SearchParams {
     long long* stats5;            // pops, expansions, pushes, heap_peak (max), los_checks
 };
 
-__device__ __forceinline__ unsigned long long entry_prio(unsigned long long e, int mode) {
-    // f_comp / g_comp / f_g_comp, grid_planner_core.cpp:55-75
-    if (mode == NSFS_MODE_F) return e >> (kKeyBits + kGBits);
-    if (mode == NSFS_MODE_G) return (e >> kKeyBits) & ((1ull << kGBits) - 1ull);
-    return e >> kKeyBits;
+// Heap storage: heap index x lives at array position x + 1 (position 0 unused), so the two children of x
+// (heap indices 2x+1, 2x+2 = positions 2x+2, 2x+3) form one 16-byte aligned pair.
+struct Prio {                     // comparator of the selected cost mode as a shift and a mask (grid_planner_core.cpp:55-75)
+    int sh;
+    unsigned long long msk;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long e) const { return (e >> sh) & msk; }
+};
+__device__ __forceinline__ Prio make_prio(int mode) {
+    Prio p;
+    if (mode == NSFS_MODE_F) { p.sh = kKeyBits + kGBits; p.msk = ~0ull; }                 // f only
+    else if (mode == NSFS_MODE_G) { p.sh = kKeyBits; p.msk = (1ull << kGBits) - 1ull; }   // g only
+    else { p.sh = kKeyBits; p.msk = ~0ull; }                                              // f, then the smaller g
+    return p;
 }
 
-// std::priority_queue::push: append, then __push_heap (stl_heap.h:135-148)
-__device__ __forceinline__ void heap_push(unsigned long long* a, long long& n, unsigned long long v, int mode) {
-    long long hole = n++;
-    const unsigned long long pv = entry_prio(v, mode);
-    while (hole > 0) {
-        const long long parent = (hole - 1) >> 1;
-        const unsigned long long e = a[parent];
-        if (!(entry_prio(e, mode) > pv)) break;
-        a[hole] = e;
-        hole = parent;
-    }
-    a[hole] = v;
+// std::priority_queue::push = push_back + __push_heap (stl_heap.h:135-148), by the whole warp (n is warp-uniform).
+// Positions fit 32 bits (heap_cap <= 8N + 16 < 2^32 / 2 for N < 2^28; larger capacities are refused by search_alloc).
+__device__ __forceinline__ void heap_push(unsigned long long* a, uint32_t& n, unsigned long long v, const Prio prio, int lane) {
+    const uint32_t pos = n + 1u;                          // array position of the new leaf
+    const unsigned long long pv = prio(v);
+    const uint32_t q = pos >> lane;                       // lane L >= 1: position of the L-th ancestor (0 = above the root)
+    const bool valid = lane >= 1 && q >= 1u;
+    unsigned long long e = 0;
+    if (valid) e = a[q];
+    const unsigned rise = __ballot_sync(0xffffffffu, valid && prio(e) > pv);    // ancestor sorts after v: it moves down
+    const int m = __ffs(~(rise >> 1)) - 1;                // length of the run of such ancestors starting at the parent
+    if (lane >= 1 && lane <= m) a[pos >> (lane - 1)] = e;
+    if (lane == 0) a[pos >> m] = v;
+    n = n + 1u;
+    __syncwarp();
 }
 
-// top() then pop(): __pop_heap -> __adjust_heap (stl_heap.h:224-262) -> __push_heap, then pop_back
-__device__ __forceinline__ unsigned long long heap_pop(unsigned long long* a, long long& n, int mode) {
-    const unsigned long long top = a[0];
-    const long long len = n - 1;
-    if (len > 0) {
-        const unsigned long long v = a[len];
-        long long hole = 0, child = 0;
-        while (child < (len - 1) / 2) {
-            child = 2 * (child + 1);
-            const unsigned long long r = a[child], l = a[child - 1];
-            unsigned long long pick = r;
-            if (entry_prio(r, mode) > entry_prio(l, mode)) { child--; pick = l; }
-            a[hole] = pick;
-            hole = child;
-        }
-        if ((len & 1) == 0 && child == (len - 2) / 2) {
-            child = 2 * (child + 1);
-            a[hole] = a[child - 1];
-            hole = child - 1;
-        }
-        const unsigned long long pv = entry_prio(v, mode);
-        while (hole > 0) {
-            const long long parent = (hole - 1) >> 1;
-            const unsigned long long e = a[parent];
-            if (!(entry_prio(e, mode) > pv)) break;
-            a[hole] = e;
-            hole = parent;
-        }
-        a[hole] = v;
-    }
+struct LaneNode {                 // my internal node of a 5-level subtree: level r (0..4), offset o within the level
+    int r;
+    uint32_t o;
+};
+__device__ __forceinline__ LaneNode lane_node(int lane) {
+    LaneNode ln;
+    ln.r = 31 - __clz(lane + 1);
+    ln.o = (uint32_t)(lane + 1) - (1u << ln.r);
+    return ln;
+}
+
+// top() + pop() = __pop_heap -> __adjust_heap -> __push_heap (stl_heap.h:224-262), by the whole warp.
+__device__ __forceinline__ void heap_pop(unsigned long long* a, uint32_t& n, const Prio prio, int lane, const LaneNode ln) {
+    const uint32_t len = n - 1u;                          // elements left after the pop
     n = len;
-    return top;
+    if (len == 0u) return;
+    const unsigned long long v = a[len + 1u];             // the displaced last element
+    const unsigned long long pv = prio(v);
+    uint32_t c1 = 1u;                                     // position (= heap index + 1) of the hole
+    for (;;) {
+        const uint32_t pos = (c1 << ln.r) + ln.o;         // position of my node; its children sit at positions 2*pos, 2*pos + 1
+        const uint32_t lpos = 2u * pos;                   // left child's position; it exists iff its heap index lpos-1 < len
+        const bool has = lane < 31 && (c1 >> (30 - ln.r)) == 0u && lpos <= len;   // (the shift test keeps pos from wrapping)
+        ulonglong2 ch = make_ulonglong2(0ull, 0ull);
+        if (has) ch = *reinterpret_cast<const ulonglong2*>(a + lpos);
+        // __adjust_heap: take the right child unless it sorts after the left one; a lone left child is taken as is
+        const bool left = !(lpos + 1u <= len) || prio(ch.y) > prio(ch.x);
+        const unsigned long long pick = left ? ch.x : ch.y;
+        const bool stop = !has || prio(pick) > pv;        // the displaced element comes to rest in my node
+        const unsigned m_left = __ballot_sync(0xffffffffu, left);
+        const unsigned m_stop = __ballot_sync(0xffffffffu, stop);
+        uint32_t node = 0, steps = 0, path = 0;
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) {
+            if ((m_stop >> node) & 1u) break;
+            path |= 1u << node;
+            node = 2u * node + 2u - ((m_left >> node) & 1u);
+            ++steps;
+        }
+        if ((path >> lane) & 1u) a[pos] = pick;           // the picked child moves up into my node
+        const int rq = 31 - __clz(node + 1u);
+        const uint32_t npos = (c1 << rq) + (node + 1u - (1u << rq));
+        if (steps < 5u) {
+            if (lane == 0) a[npos] = v;
+            break;
+        }
+        c1 = npos;                                        // five levels down and still sinking
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ double cell_g(const uint4& c) { return __hiloint2double((int)c.y, (int)c.x); }
@@ -109,9 +149,9 @@ __device__ __forceinline__ uint4 make_cell(double g, uint32_t parent, uint32_t t
 
 // dist_oct(Index, Index), bot_utils.cpp:44-65 with the line-47 slip: both deltas are taken against the ROW.
 __device__ __forceinline__ double h_oct(int i, int gi, int gj) {
-    const double ax = fabs((double)gi - (double)i), ay = fabs((double)gj - (double)i);
-    const double ord = ax > ay ? ay : ax, card = ax > ay ? ax - ay : ay - ax;
-    return __dadd_rn(__dmul_rn(ord, kSqrt2D), card);          // no FMA: the host computes mul then add
+    const int ax = abs(gi - i), ay = abs(gj - i);              // integers: |.|, min and difference are exact either way
+    const int ord = min(ax, ay), card = abs(ax - ay);
+    return __dadd_rn(__dmul_rn((double)ord, kSqrt2D), (double)card);   // no FMA: the host computes mul then add
 }
 // dist_euc(Index, Index), bot_utils.cpp:72-87
 __device__ __forceinline__ double d_euc(int ai, int aj, int bi, int bj) {
@@ -127,7 +167,7 @@ __device__ __forceinline__ double heuristic(int i, int j, int gi, int gj) {
 }
 
 // pushToOpenList, grid_planner_core.cpp:385-391: f = (mode == "g") ? 0 : g + h, both truncated to int
-__device__ __forceinline__ unsigned long long make_entry(double g, double h, long long key, int mode) {
+__device__ __forceinline__ unsigned long long make_entry(double g, double h, uint32_t key, int mode) {
     const double f = (mode == NSFS_MODE_G) ? 0.0 : __dadd_rn(g, h);
     const unsigned long long fi = (unsigned long long)(unsigned)__double2int_rz(f);
     const unsigned long long gi = (unsigned long long)(unsigned)__double2int_rz(g);
@@ -159,14 +199,17 @@ __device__ __forceinline__ bool warp_los(const uint32_t* __restrict__ free_bits,
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(SearchParams p) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SEARCH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (slot >= p.slots) return;
     const int W = p.W, H = p.H, mode = p.mode;
     const long long N = p.N;
     uint4* cells = p.cells + (size_t)slot * (size_t)N;
-    unsigned long long* heap = p.heap + (size_t)slot * (size_t)p.heap_cap;
+    unsigned long long* heap = p.heap + (size_t)slot * (size_t)p.heap_stride;
+    const Prio prio = make_prio(mode);
+    const LaneNode ln = lane_node(lane);
+    const uint32_t uW = (uint32_t)W, uN = (uint32_t)N;       // N < 2^29 (nsfs_create)
     uint32_t epoch = p.epoch[slot];
     const bool serial = W < 3;      // for W < 3 two directions can alias one key: evaluate them one after another
 
@@ -181,44 +224,60 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
         if (ALGO == kAlgoFallback) { si = p.q[2 * qi]; sj = p.q[2 * qi + 1]; }
         else { si = p.q[4 * qi]; sj = p.q[4 * qi + 1]; gi = p.q[4 * qi + 2]; gj = p.q[4 * qi + 3]; }
 
-        long long n = 0;                       // open-list length (warp-uniform)
+        uint32_t n = 0;                        // open-list length (warp-uniform)
         long long pops = 0, expansions = 0, pushes = 0, peak = 0, los_checks = 0;
         int status = NSFS_OK;
         bool found = false;
-        long long k_found = -1;
-        const long long ks = (long long)si * W + sj;
-        const long long kg = (gi >= 0 && gi < H && gj >= 0 && gj < W) ? (long long)gi * W + gj : -1;
+        uint32_t k_found = 0;
+        const uint32_t ks = (uint32_t)(si * W + sj);
+        const uint32_t kg = (gi >= 0 && gi < H && gj >= 0 && gj < W) ? (uint32_t)(gi * W + gj) : 0xffffffffu;   // no cell has this key
 
         if (si < 0 || si >= H || sj < 0 || sj >= W) {
             status = NSFS_E_ARG;               // the reference indexes nodes[] out of bounds here (undefined behaviour)
         } else {
-            if (lane == 0) {
-                cells[ks] = make_cell(0.0, (uint32_t)ks, epoch << 1);
-                heap_push(heap, n, make_entry(0.0, heuristic<ALGO>(si, sj, gi, gj), ks, mode), mode);
-            }
-            n = 1; pushes = 1; peak = 1;
+            if (lane == 0) __stcg(cells + ks, make_cell(0.0, ks, epoch << 1));
             __syncwarp();
+            heap_push(heap, n, make_entry(0.0, heuristic<ALGO>(si, sj, gi, gj), ks, mode), prio, lane);
+            pushes = 1; peak = 1;
         }
 
         while (status == NSFS_OK && n > 0) {
             // ---- pop (astar.cpp:56) --------------------------------------------------------------------
-            unsigned long long top = 0;
-            if (lane == 0) top = heap_pop(heap, n, mode);
-            top = __shfl_sync(0xffffffffu, top, 0);
-            n = __shfl_sync(0xffffffffu, n, 0);
+            const unsigned long long top = heap[1];            // same address in every lane: one broadcast load
+            const uint32_t ku = (uint32_t)(top & kKeyMask);
+            const int i = (int)(ku / uW), j = (int)(ku - (uint32_t)i * uW);
+            // Everything the expansion reads depends only on ku: issue those loads now, use them after the sift-down.
+            //   lanes 0..7  record of neighbour d (key range only; whether d is passable comes with the mask)
+            //   lane 8      record of the popped cell          lane 9   its edge mask
+            // my neighbour (lanes 0..7): flat key, and its (row, column) without another division - a column that leaves
+            // [0, W) wraps into the next / previous row, which is exactly what the flat key does
+            const int dd = lane & 7;
+            const uint32_t kv_mine = ku + (uint32_t)(nb_di(dd) * W + nb_dj(dd));
+            int vi_mine = i + nb_di(dd), vj_mine = j + nb_dj(dd);
+            if (vj_mine >= W) { vj_mine -= W; vi_mine++; } else if (vj_mine < 0) { vj_mine += W; vi_mine--; }
+            uint4 pre = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t pre_mask = 0;
+            if (lane < 8) {
+                if (kv_mine < uN) pre = __ldcg(cells + kv_mine);       // unsigned: a negative key wraps above N
+            } else if (lane == 8) {
+                pre = __ldcg(cells + ku);
+            } else if (lane == 9) {
+                pre_mask = __ldg(p.out_mask + ku);
+            }
+            heap_pop(heap, n, prio, lane, ln);
             pops++;
-            const long long ku = (long long)(top & kKeyMask);
-            const uint4 cu = cells[ku];        // same address in every lane: one broadcast load
+            uint4 cu;
+            cu.x = __shfl_sync(0xffffffffu, pre.x, 8); cu.y = __shfl_sync(0xffffffffu, pre.y, 8);
+            cu.z = __shfl_sync(0xffffffffu, pre.z, 8); cu.w = __shfl_sync(0xffffffffu, pre.w, 8);
             if (cu.w & 1u) continue;           // stale entry (astar.cpp:59-62)
-            if (lane == 0) cells[ku].w = cu.w | 1u;
+            if (lane == 0) __stcg(&cells[ku].w, cu.w | 1u);
             expansions++;
-            const int i = (int)(ku / W), j = (int)(ku - (long long)i * W);
             if (ALGO == kAlgoFallback) {
                 if (bit_at(p.free_bits, ku)) { found = true; k_found = ku; break; }     // djikstra.cpp:205-211
-            } else if (i == gi && j == gj) { found = true; k_found = ku; break; }       // astar.cpp:68
+            } else if (ku == kg) { found = true; k_found = ku; break; }                 // astar.cpp:68
 
             const double gu = cell_g(cu);
-            const uint32_t om = p.out_mask[ku];
+            const uint32_t om = __shfl_sync(0xffffffffu, pre_mask, 9);
             if (om & kThrowBit) { status = NSFS_E_RANGE; break; }                       // vector::at throws (R6)
 
             // ---- neighbours (astar.cpp:89-124 / djikstra.cpp:214-267) ------------------------------------
@@ -234,15 +293,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
             double gp = 0.0;
             int pi = 0, pj = 0;
             if (ALGO == NSFS_THETASTAR) {
-                gp = cell_g(cells[pkey]);
+                gp = cell_g(__ldcg(cells + pkey));
                 pi = (int)(pkey / (uint32_t)W); pj = (int)(pkey - (uint32_t)pi * (uint32_t)W);
             }
             uint32_t los_bits = 0;
             if (ALGO == NSFS_THETASTAR) {
                 for (int d = 0; d < 8; ++d) {
                     if (!((om >> d) & 1u)) continue;
-                    const long long kv = ku + nb_off(d, W);
-                    const int vi = (int)(kv / W), vj = (int)(kv - (long long)vi * W);
+                    const int vi = __shfl_sync(0xffffffffu, vi_mine, d), vj = __shfl_sync(0xffffffffu, vj_mine, d);
                     los_checks++;
                     if (warp_los(p.free_bits, W, pi, pj, vi, vj, lane)) los_bits |= 1u << d;
                 }
@@ -252,7 +310,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
                 const int d = lane;
                 const bool mine = serial ? (lane == round) : (lane < 8);
                 bool relax = false;
-                long long kv = 0;
+                const uint32_t kv = kv_mine;
                 double cand = 0.0;
                 uint32_t par = (uint32_t)ku;
                 if (mine) {
@@ -260,8 +318,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
                     if (ALGO == kAlgoFallback) considered = (rowok >> d) & 1u;
                     else considered = (om >> d) & 1u;
                     if (considered) {
-                        kv = ku + nb_off(d, W);
-                        const uint4 cv = cells[kv];
+                        const uint4 cv = serial ? __ldcg(cells + kv) : pre;      // W < 3: an earlier round may have re-labelled it
                         const bool valid = (cv.w >> 1) == epoch;
                         const double gv = valid ? cell_g(cv) : kInfD;
                         if (ALGO == kAlgoFallback) {
@@ -273,14 +330,13 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
                                 cand = __dadd_rn(gu, card ? 1.0 : kSqrt2D);
                             }
                         } else if (ALGO == NSFS_THETASTAR) {
-                            const int vi = (int)(kv / W), vj = (int)(kv - (long long)vi * W);
-                            if ((los_bits >> d) & 1u) { cand = __dadd_rn(gp, d_euc(pi, pj, vi, vj)); par = pkey; }
-                            else cand = __dadd_rn(gu, d_euc(i, j, vi, vj));
+                            if ((los_bits >> d) & 1u) { cand = __dadd_rn(gp, d_euc(pi, pj, vi_mine, vj_mine)); par = pkey; }
+                            else cand = __dadd_rn(gu, d_euc(i, j, vi_mine, vj_mine));
                         } else {
                             cand = __dadd_rn(gu, ((om >> (8 + d)) & 1u) && d ? kSqrt2D : 1.0);     // astar.cpp:104-107
                         }
                         relax = gv > __dadd_rn(cand, kSlack);                                         // astar.cpp:116
-                        if (relax) cells[kv] = make_cell(cand, par, (epoch << 1) | (valid ? (cv.w & 1u) : 0u));
+                        if (relax) __stcg(cells + kv, make_cell(cand, par, (epoch << 1) | (valid ? (cv.w & 1u) : 0u)));
                     }
                 }
                 uint32_t rb = __ballot_sync(0xffffffffu, relax);
@@ -288,14 +344,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
                 while (rb) {
                     const int src = __ffs(rb) - 1;
                     rb &= rb - 1;
-                    const long long pk = __shfl_sync(0xffffffffu, kv, src);
+                    const uint32_t pk = __shfl_sync(0xffffffffu, kv, src);
                     const double pg = __shfl_sync(0xffffffffu, cand, src);
-                    if (n >= p.heap_cap) { status = NSFS_E_HEAP; break; }
-                    if (lane == 0) {
-                        const int vi = (int)(pk / W), vj = (int)(pk - (long long)vi * W);
-                        heap_push(heap, n, make_entry(pg, heuristic<ALGO>(vi, vj, gi, gj), pk, mode), mode);
-                    }
-                    n = __shfl_sync(0xffffffffu, n, 0);
+                    if ((long long)n >= p.heap_cap) { status = NSFS_E_HEAP; break; }
+                    const int vi = __shfl_sync(0xffffffffu, vi_mine, src), vj = __shfl_sync(0xffffffffu, vj_mine, src);
+                    heap_push(heap, n, make_entry(pg, heuristic<ALGO>(vi, vj, gi, gj), pk, mode), prio, lane);
                     pushes++;
                     if (n > peak) peak = n;
                 }
@@ -308,25 +361,25 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
         if (lane == 0) {
             int plen = 1;
             if (ALGO == kAlgoFallback) {
-                const long long kr = (found && status == NSFS_OK) ? k_found : ks;     // failure => the input cell (djikstra.cpp:272)
-                if (p.paths) { p.paths[2 * qi] = (int)(kr / W); p.paths[2 * qi + 1] = (int)(kr % W); }
+                const uint32_t kr = (found && status == NSFS_OK) ? k_found : ks;      // failure => the input cell (djikstra.cpp:272)
+                if (p.paths) { p.paths[2 * qi] = (int)(kr / uW); p.paths[2 * qi + 1] = (int)(kr % uW); }
             } else if (status == NSFS_OK) {
                 int32_t* out = p.paths ? p.paths + (size_t)qi * p.path_cap * 2 : nullptr;
                 if (found) {                                                        // back-track (astar.cpp:70-82)
-                    long long k = kg;
+                    uint32_t k = kg;
                     plen = 0;
                     for (;;) {
-                        if (out && plen < p.path_cap) { out[2 * plen] = (int)(k / W); out[2 * plen + 1] = (int)(k % W); }
+                        if (out && plen < p.path_cap) { out[2 * plen] = (int)(k / uW); out[2 * plen + 1] = (int)(k % uW); }
                         plen++;
-                        if (k == ks || plen > N) break;
-                        k = cells[k].z;
+                        if (k == ks || (long long)plen > N) break;
+                        k = __ldcg(cells + k).z;
                     }
                 } else if (out && p.path_cap > 0) {                                 // astar.cpp:129-135
                     out[0] = si; out[1] = sj;
                 }
                 if (p.g_goal) {
                     double gg = kInfD;
-                    if (kg >= 0) { const uint4 c = cells[kg]; if ((c.w >> 1) == epoch) gg = cell_g(c); }
+                    if (kg != 0xffffffffu) { const uint4 c = __ldcg(cells + kg); if ((c.w >> 1) == epoch) gg = cell_g(c); }
                     p.g_goal[qi] = gg;
                 }
             } else if (p.g_goal && ALGO != kAlgoFallback) {
@@ -352,12 +405,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) search_kernel(Sea
 int search_alloc(nsfs_planner* h, int want_slots) {
     SearchWork& s = h->search;
     long long heap_cap = h->opt_heap_cap > 0 ? h->opt_heap_cap : h->N + 8;
+    if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;            // heap positions are 32-bit
     if (want_slots < 1) want_slots = 1;
     if (s.cells && s.slots >= want_slots && s.heap_cap >= heap_cap) return NSFS_OK;
     search_free(h);
     size_t free_b = 0, total_b = 0;
     NSFS_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_slot = (size_t)h->N * sizeof(uint4) + (size_t)heap_cap * sizeof(unsigned long long);
+    const long long heap_stride = (heap_cap + 5) & ~1ll;
+    const size_t per_slot = (size_t)h->N * sizeof(uint4) + (size_t)heap_stride * sizeof(unsigned long long);
     long long fit = (long long)((double)free_b * 0.80 / (double)per_slot);
     long long cap = h->opt_max_slots > 0 ? h->opt_max_slots : (long long)h->sm_count * 32;
     long long slots = want_slots;
@@ -365,7 +420,7 @@ int search_alloc(nsfs_planner* h, int want_slots) {
     if (slots > fit) slots = fit;
     if (slots < 1) return NSFS_E_NOMEM;
     NSFS_CUDA_TRY(h, cudaMalloc(&s.cells, (size_t)slots * (size_t)h->N * sizeof(uint4)));
-    NSFS_CUDA_TRY(h, cudaMalloc(&s.heap, (size_t)slots * (size_t)heap_cap * sizeof(unsigned long long)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.heap, (size_t)slots * (size_t)heap_stride * sizeof(unsigned long long)));
     NSFS_CUDA_TRY(h, cudaMalloc(&s.epoch, (size_t)slots * sizeof(uint32_t)));
     NSFS_CUDA_TRY(h, cudaMalloc(&s.work_counter, sizeof(int)));
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * (size_t)h->N * sizeof(uint4), h->stream));
@@ -391,7 +446,7 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
     SearchParams p;
     p.free_bits = h->d_free; p.infl_bits = h->d_inflated; p.out_mask = h->d_out_mask;
     p.cells = s.cells; p.heap = s.heap; p.epoch = s.epoch; p.work_counter = s.work_counter;
-    p.H = h->H; p.W = h->W; p.N = h->N; p.heap_cap = s.heap_cap;
+    p.H = h->H; p.W = h->W; p.N = h->N; p.heap_cap = s.heap_cap; p.heap_stride = (s.heap_cap + 5) & ~1ll;
     p.slots = nq < s.slots ? nq : s.slots;
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;     // unknown => fg (grid_planner_core.cpp:274-281)
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
