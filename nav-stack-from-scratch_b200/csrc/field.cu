@@ -24,16 +24,20 @@ namespace cg = cooperative_groups;
 
 namespace nsfs {
 
-constexpr int TS = 64;                 // tile side in cells
+#ifndef NSFS_TS
+#define NSFS_TS 64
+#endif
+constexpr int TS = NSFS_TS;            // tile side in cells (64: one 1024-thread block per SM; 32: four 256-thread blocks per SM)
 constexpr int SBW = 8, SBH = 4;        // sub-block: 8 columns x 4 rows = one lane per cell
-constexpr int SB_X = TS / SBW;         // 8
-constexpr int SB_Y = TS / SBH;         // 16
-constexpr int NSB = SB_X * SB_Y;       // 128 sub-blocks per tile
-constexpr int FIELD_THREADS = 1024;    // 32 warps, warp w owns sub-blocks w, w+32, w+64, w+96
-constexpr int FIELD_WARPS = FIELD_THREADS / 32;
-constexpr int SB_PER_WARP = NSB / FIELD_WARPS;
-static_assert(SB_PER_WARP == 4 && FIELD_WARPS == 32, "a warp polls its four flags as one word; the finisher reads 32 words");
-constexpr int SROW = 72;               // smem row stride in floats; 72 % 32 == 8 => the 4 rows of a sub-block use disjoint banks
+constexpr int SB_X = TS / SBW;
+constexpr int SB_Y = TS / SBH;
+constexpr int NSB = SB_X * SB_Y;       // sub-blocks per tile (128 / 32)
+constexpr int SB_PER_WARP = 4;         // warp w owns sub-blocks w, w + W, w + 2W, w + 3W (W = FIELD_WARPS)
+constexpr int FIELD_WARPS = NSB / SB_PER_WARP;
+constexpr int FIELD_THREADS = FIELD_WARPS * 32;
+constexpr int FIELD_BLOCKS_PER_SM = 1024 / FIELD_THREADS;
+static_assert(FIELD_WARPS <= 32 && NSB % SB_PER_WARP == 0, "a warp polls its four flags as one word; the finisher reads one word per warp");
+constexpr int SROW = TS + 8;           // smem row stride in floats; SROW % 32 == 8 => the 4 rows of a sub-block use disjoint banks
 constexpr int SCOL0 = 4;               // smem column of tile column 0 (halo column -1 at 3)
 constexpr int SROWS = TS + 2;
 constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending update" (non-negative floats order like their bits)
@@ -85,6 +89,10 @@ __global__ void field_seed_kernel(FieldParams p, const uint32_t* __restrict__ fr
     int pend = 0;
     auto seed_tile = [&](int t) { if (p.tile_key[t] == kNoKey) ++pend; p.tile_key[t] = 0u; };
     seed_tile(tile_of(ks));
+    for (int d = 0; d < 8; ++d) {              // and the tiles that read the source as halo (it never "changes" in a visit, so nobody posts it)
+        const long long kv = ks + nb_off(d, p.W);
+        if (kv >= 0 && kv < p.N) seed_tile(tile_of(kv));
+    }
     if (!bit_at(free_bits, ks)) {
         const uint32_t om = out_mask[ks];
         for (int d = 0; d < 8; ++d) {
@@ -112,9 +120,20 @@ __global__ void __launch_bounds__(256) field_inject_kernel(FieldParams p, long l
         if (v < old) {
             p.g[k] = v;
             better = true;
-            const int tile = (int)(k / p.W) / TS * p.tiles_x + (int)(k % p.W) / TS;
-            const uint32_t was = atomicMin(p.tile_key + tile, __float_as_uint(v));
-            if (was == kNoKey) atomicAdd(p.counts + 1, 1);
+            // pending: the tile that holds the cell AND every tile that reads it as halo, i.e. the tiles of its out-neighbours
+            // (flat-key arithmetic, so the column wrap of the reference's stencil is covered too)
+            const uint32_t key = __float_as_uint(v);
+            int last = -1;
+#pragma unroll
+            for (int d = -1; d < 8; ++d) {
+                const long long kv = d < 0 ? k : k + nb_off(d, p.W);
+                if (kv < 0 || kv >= p.N) continue;
+                const int tile = (int)(kv / p.W) / TS * p.tiles_x + (int)(kv % p.W) / TS;
+                if (tile == last) continue;
+                last = tile;
+                const uint32_t was = atomicMin(p.tile_key + tile, key);
+                if (was == kNoKey) atomicAdd(p.counts + 1, 1);
+            }
         }
     }
     const uint32_t b = __ballot_sync(0xffffffffu, better);
@@ -237,7 +256,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
             old = __shfl_sync(0xffffffffu, old, 0);
             counted_idle = true;
             if (old == FIELD_WARPS - 1) {                             // every warp is idle-counted: verify and finish
-                const uint32_t f4 = reinterpret_cast<const volatile uint32_t*>(s_flag_)[lane];
+                const uint32_t f4 = lane < FIELD_WARPS ? reinterpret_cast<const volatile uint32_t*>(s_flag_)[lane] : 0u;
                 const bool any = __any_sync(0xffffffffu, f4 != 0u);
                 if (!any && s_ctl[0] == FIELD_WARPS && lane == 0) s_ctl[1] = 1;
             }
@@ -365,7 +384,7 @@ __device__ __forceinline__ void select_tiles(const FieldParams& p, int* s_int) {
     if (tid == 0) p.counts[0] = s_int[1];
 }
 
-__global__ void __launch_bounds__(FIELD_THREADS, 1) field_solve_kernel(FieldParams p) {
+__global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solve_kernel(FieldParams p) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
@@ -410,7 +429,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) field_solve_kernel(FieldPara
 // smallest key, relaxes it within the band [key, key + delta], and posts keys to the tiles whose halo it moved.
 // counts[1] = tiles with a pending key + visits in flight; the kernel ends when it reaches zero.  Every spin loop has a
 // bail-out (counts[4] bit 1) so the kernel cannot hang.
-__global__ void __launch_bounds__(FIELD_THREADS, 1) field_solve_async_kernel(FieldParams p) {
+__global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solve_async_kernel(FieldParams p) {
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
     __shared__ int s_ctl[2];

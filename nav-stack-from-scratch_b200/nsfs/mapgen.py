@@ -61,6 +61,35 @@ def synth_map(H: int, W: int, p_occ: float, seed: int, inflated: bool = False, f
     return infl, lo
 
 
+def synth_map_rows(H: int, W: int, p_occ: float, seed: int, row_lo: int, row_hi: int, frame: bool = True):
+    """Rows [row_lo, row_hi) of the raw (not inflated) ``synth_map(H, W, p_occ, seed)`` without building the whole map.
+
+    MT19937 cannot jump ahead, so the stream is generated from the start in chunks and dropped until ``row_lo``; memory
+    stays at a few rows' worth plus the result (a 16384 x 16384 map would otherwise need ~10 GB of temporaries per rank).
+    Returns (infl, lo) int32 [row_hi - row_lo, W], bit-identical to the same rows of synth_map (tests/test_mapgen.py)."""
+    rs = np.random.RandomState(int(seed) & 0xFFFFFFFF)
+    rows_per_chunk = max(1, (1 << 22) // max(W, 1))
+    occ = np.zeros((row_hi - row_lo, W), bool)
+    r = 0
+    while r < row_hi:
+        nr = min(rows_per_chunk, row_hi - r)
+        raw = rs.randint(0, 2**32, size=2 * nr * W, dtype=np.uint32)
+        a, b = max(r, row_lo), r + nr
+        if b > a:
+            blk = raw[2 * (a - r) * W:].astype(np.float64)
+            u = (blk[0::2] + blk[1::2] * 4294967296.0) / 18446744073709551616.0
+            occ[a - row_lo:b - row_lo] = (np.minimum(u, np.nextafter(1.0, 0.0)) < p_occ).reshape(b - a, W)
+        r += nr
+    if frame:
+        occ[:, 0] = occ[:, -1] = True
+        if row_lo == 0:
+            occ[0, :] = True
+        if row_hi == H:
+            occ[-1, :] = True
+    lo = np.where(occ, LO_OCCUPIED, 0).astype(np.int32)
+    return occ.astype(np.int32), lo
+
+
 def free_mask(infl: np.ndarray, lo: np.ndarray, lo_thresh: int = LO_THRESH) -> np.ndarray:
     return (infl <= 0) & (lo <= lo_thresh)
 

@@ -43,6 +43,41 @@ def test_sharded_field_is_bit_identical_to_one_handle(gpu_lib, spec):
         s.solver.close()
 
 
+def test_shard_boundaries_on_tile_boundaries(gpu_lib):
+    """Shard edges that coincide with the solver's 64-cell tile edges: an injected ghost row must wake the tiles that
+    read it as halo, not only the tile that holds it (16384 rows over 2/4/8 ranks is exactly this case)."""
+    infl, lo = mapgen.synth_map(256, 192, 0.10, 55)
+    src = tuple(mapgen.sample_free_cells(infl[130:250], lo[130:250], 1, 55)[0] + np.array([130, 0]))
+    want = _mono(gpu_lib, infl, lo, src)
+    for world in (2, 4):
+        part = sf.RowPartition(256, 192, world)
+        assert all(b % 64 == 0 for b in part.bounds)
+        shards = [sf.make_gpu_shard(part, r, infl, lo) for r in range(world)]
+        out = sf.solve_in_process(shards, src)
+        g = np.concatenate([s.owned_rows().cpu().numpy() for s in shards])
+        assert np.array_equal(g, want["g"])
+        assert sum(r["reached"] for r in out["results"]) == want["reached"]
+        for s in shards:
+            s.solver.close()
+
+
+def test_source_on_a_tile_edge_with_its_tile_walled_off(gpu_lib, oracle_mod):
+    """The source cell never changes during a visit, so the tiles that read it as halo must be seeded explicitly."""
+    infl, lo = mapgen.synth_map(192, 192, 0.0, 56)
+    src = (64, 70)                                   # first row of tile row 1
+    for c in ((64, 69), (64, 71), (65, 69), (65, 70), (65, 71)):      # every in-tile neighbour blocked: only row 63 is open
+        infl[c] = 1
+        lo[c] = 20
+    P = gpu_lib.Planner(192, 192)
+    P.set_map(infl, lo)
+    r = P.field(src)
+    o = oracle_mod.Oracle(infl, lo).field(src)
+    assert r["status"] == 0 and o["status"] == 0
+    assert np.array_equal(r["g"] < 1e5, o["g"] < 1e5) and r["reached"] == int((o["g"] < 1e5).sum()) > 30000
+    assert np.abs(r["g"] - o["g"]).max() <= 1e-5 * o["g"][o["g"] < 1e5].max()
+    P.close()
+
+
 def test_shard_without_source_and_unreachable_rows(gpu_lib):
     """A wall across the map: the shards beyond it stay at 1e5 and the loop still terminates."""
     infl, lo = mapgen.synth_map(200, 160, 0.05, 54)

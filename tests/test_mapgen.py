@@ -37,3 +37,10 @@ def test_samplers():
     assert not free[bad[:, 0], bad[:, 1]].any() and bad.min() >= 2
     s = mapgen.field_source(infl, lo)
     assert free[s]
+
+
+def test_row_range_generator_matches_the_whole_map():
+    infl, lo = mapgen.synth_map(301, 257, 0.1, 77)
+    for a, b in ((0, 301), (0, 17), (120, 200), (290, 301)):
+        i2, l2 = mapgen.synth_map_rows(301, 257, 0.1, 77, a, b)
+        assert np.array_equal(i2, infl[a:b]) and np.array_equal(l2, lo[a:b])
