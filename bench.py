@@ -304,7 +304,7 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
             r = P.field_device((src[0] - a, src[1]))
             return dict(reached=r["reached"], rounds=1, kernel_ms=r["stats"]["main_kernel_ms"], dev_ms=r["stats"]["gpu_ms"],
                         visits=r["stats"]["tile_visits"])
-        out = sf.solve_distributed(shard, src, dist, dev)
+        out = sf.solve_distributed(shard, src, dist, dev, band=args.band if args.band > 0 else None)
         return dict(reached=out["result"]["reached"], rounds=out["rounds"],
                     kernel_ms=sum(s["main_kernel_ms"] for s in shard.solver.stats),
                     dev_ms=sum(s["gpu_ms"] for s in shard.solver.stats) + out["result"]["stats"]["gpu_ms"],
@@ -375,7 +375,7 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "units_per_step": "1 field over all ranks",
-                   "partition": f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, NCCL send/recv + 1 all-reduce per round" if world > 1 else "single handle",
+                   "partition": f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, NCCL send/recv + 1 all-reduce per round, band {args.band:g}" if world > 1 else "single handle",
                    "l2": "flushed between timed steps (256 MiB fill)",
                    "timing": "wall clock between cuda synchronize + barrier on both sides, max over ranks (the step spans several kernels, NCCL and host round control)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -611,6 +611,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=16384, help="queries per step per GPU (c4); keep it >= 3x the 4736 query slots")
+    ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

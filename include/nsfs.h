@@ -123,12 +123,18 @@ int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n
  * (local row numbers, hi exclusive, 0 = unset).  Then per solve:
  *   nsfs_field_begin(h, si, sj)            g = 1e5 everywhere; (si, sj) local source, or si < 0 when another shard owns it
  *   repeat { nsfs_field_inject_rows(..)    g[row0 .. row0+nrows) = min(g, vals): ghost rows received from a neighbour shard
- *            nsfs_field_relax(h, st) }     relax to the local fixed point; the caller exchanges boundary rows between shards
+ *            nsfs_field_relax[_until](..) } relax to the local fixed point (or up to a cost cap); the caller exchanges
+ *                                          boundary rows between shards
  *   nsfs_field_finish(h, st)               predecessor field + reached count of the counted rows; then nsfs_field_device*
  * All three leave results on the device (nsfs_field_device's pointers stay valid). */
 int nsfs_field_begin(nsfs_t* h, int si, int sj);
 int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, int* n_improved);   /* device values */
 int nsfs_field_relax(nsfs_t* h, nsfs_stats* st);
+/* Same, but nothing is relaxed beyond the cost `cap`: tiles whose smallest pending value exceeds it stay pending.
+ * min_pending = the smallest value still pending afterwards (+inf when the shard is at its fixed point).  Lets all
+ * shards of a partitioned map advance band by band (cap = global min pending + band width) instead of one after another. */
+int nsfs_field_relax_until(nsfs_t* h, float cap, float* min_pending, nsfs_stats* st);
+int nsfs_field_min_pending(nsfs_t* h, float* min_pending);   /* e.g. after nsfs_field_inject_rows */
 int nsfs_field_finish(nsfs_t* h, nsfs_stats* st);
 int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred);   /* valid after nsfs_field_begin */
 

@@ -399,25 +399,45 @@ static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (st) {
         memset(st, 0, sizeof(*st));
-        st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5]; st->pops = counts[6];
+        st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5];
         st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
     }
     if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }
+    uint32_t kb = (uint32_t)counts[6];                  // smallest key still pending (float bits; +inf bits = none)
+    memcpy(&h->field.min_pending, &kb, sizeof(kb));
     if (counts[4] & 1) return NSFS_E_RANGE; // a reached cell's expansion throws in the reference
     return NSFS_OK;
 }
 
-int nsfs_field_relax(nsfs_t* h, nsfs_stats* st) {
+int nsfs_field_relax_until(nsfs_t* h, float cap, float* min_pending, nsfs_stats* st) {
     int rc = enter(h, true);
     if (rc != NSFS_OK) return rc;
     if (!h->field.begun) return NSFS_E_NOFIELD;
+    if (!(cap >= 0.f)) return NSFS_E_ARG;
     const long long launches0 = h->launches;
     Timer tm(h);
-    if ((rc = launch_field_relax(h)) != NSFS_OK) return rc;
+    if ((rc = launch_field_relax(h, cap)) != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
-    return field_read_counts(h, st, launches0, ms, tm.main_kernel_ms());
+    rc = field_read_counts(h, st, launches0, ms, tm.main_kernel_ms());
+    if (min_pending) *min_pending = h->field.min_pending;
+    return rc;
 }
+
+int nsfs_field_min_pending(nsfs_t* h, float* min_pending) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    if ((rc = launch_field_min_pending(h)) != NSFS_OK) return rc;
+    uint32_t kb = 0;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&kb, h->field.counts + 6, sizeof(kb), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(&h->field.min_pending, &kb, sizeof(kb));
+    if (min_pending) *min_pending = h->field.min_pending;
+    return NSFS_OK;
+}
+
+int nsfs_field_relax(nsfs_t* h, nsfs_stats* st) { return nsfs_field_relax_until(h, 3.4e38f, nullptr, st); }
 
 int nsfs_field_finish(nsfs_t* h, nsfs_stats* st) {
     int rc = enter(h, true);

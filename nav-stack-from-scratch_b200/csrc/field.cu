@@ -17,6 +17,7 @@
 // shared memory), so the work follows the wavefront instead of sweeping the whole tile.
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstring>
 
 #include "nsfs_internal.cuh"
 
@@ -61,6 +62,8 @@ struct FieldParams {
     int inner;            // warp-local relaxations of an active sub-block per block-wide sweep
     float delta;          // width of the cost band [.., thr] the wavefront may advance into per round (delta-stepping)
     float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
+    uint32_t cap;         // float bits: tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it
+                          // (kNoKey - 1 = no cap).  Used by the multi-GPU solve to advance all shards band by band.
 };
 
 __global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* __restrict__ g, long long N,
@@ -332,7 +335,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         }
         if (target >= 0 && m != kNoKey) {
             const uint32_t old = atomicMin(p.tile_key + target, m);
-            if (ASYNC_TILES && old == kNoKey) atomicAdd(p.counts + 1, 1);     // a tile became pending
+            if (ASYNC_TILES && old > p.cap && m <= p.cap) atomicAdd(p.counts + 1, 1);     // a tile became pending (within the cap)
         }
     }
     if (tid == 0) atomicAdd(p.counts + 3, 1);
@@ -360,9 +363,9 @@ __device__ __forceinline__ void select_tiles(const FieldParams& p, int* s_int) {
     if (lane == 0 && mn != kNoKey) atomicMin((uint32_t*)s_int, mn);
     __syncthreads();
     const uint32_t gmin = (uint32_t)s_int[0];
-    if (gmin != kNoKey) {
+    if (gmin <= p.cap) {
         const float prev = __int_as_float(p.counts[7]);
-        const float thr_f = fmaxf(__uint_as_float(gmin) + p.delta, prev + p.alpha * p.delta);
+        const float thr_f = fminf(fmaxf(__uint_as_float(gmin) + p.delta, prev + p.alpha * p.delta), __uint_as_float(p.cap));
         const uint32_t thr = __float_as_uint(thr_f);
         if (tid == 0) p.counts[7] = __float_as_int(thr_f);
         for (int base = 0; base < n_tiles; base += FIELD_THREADS) {
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         unsigned long long best = ~0ull;
         for (int t = blockIdx.x + tid * gridDim.x; t < n_tiles; t += gridDim.x * FIELD_THREADS) {
             const uint32_t k = __ldcg(p.tile_key + t);
-            if (k != kNoKey) best = min(best, ((unsigned long long)k << 32) | (unsigned)t);
+            if (k <= p.cap) best = min(best, ((unsigned long long)k << 32) | (unsigned)t);
         }
         for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
         if (lane == 0 && best != ~0ull) atomicMin(&s_best, best);
@@ -466,10 +469,35 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         const int tile = (int)(pick & 0xffffffffu);
         if (tid == 0) { s_key = atomicExch(p.tile_key + tile, kNoKey); __threadfence(); }
         __syncthreads();
-        const float thr = __uint_as_float(s_key) + p.delta;
+        const float thr = fminf(__uint_as_float(s_key) + p.delta, __uint_as_float(p.cap));
         __syncthreads();
         relax_tile<true>(p, tile, thr, s, s_flag, s_ctl, s_emin);
         if (tid == 0) { __threadfence(); atomicSub(p.counts + 1, 1); }
+    }
+}
+
+// Before a (capped) solve: counts[1] = tiles whose pending key lies within the cap.  After it: counts[6] = the smallest
+// key still pending (float bits, kNoKey = none), which the multi-GPU driver all-reduces to place the next band.
+__global__ void __launch_bounds__(256) field_pending_kernel(const uint32_t* __restrict__ tile_key, int n_tiles, uint32_t cap,
+                                                            int* __restrict__ counts, int what) {
+    __shared__ uint32_t s_min;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) { s_min = kNoKey; s_cnt = 0; }
+    __syncthreads();
+    uint32_t mn = kNoKey;
+    int cnt = 0;
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        const uint32_t k = tile_key[t];
+        mn = min(mn, k);
+        cnt += k <= cap;
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, mn); atomicAdd(&s_cnt, cnt); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (what == 0) counts[1] = s_cnt;
+        else counts[6] = (int)s_min;
     }
 }
 
@@ -571,6 +599,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.idle_ns = h->opt_field_idle_ns > 0 ? (unsigned)h->opt_field_idle_ns : 1000u;
     p.delta = h->opt_field_delta > 0 ? (float)h->opt_field_delta : 128.0f;
     p.alpha = h->opt_field_alpha >= 0 ? (float)h->opt_field_alpha / 100.0f : 0.5f;
+    p.cap = kNoKey - 1u;
     return p;
 }
 
@@ -604,10 +633,14 @@ int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_val
     return NSFS_OK;
 }
 
-// Phase 3 (repeatable): relax every pending tile until nothing is pending.
-int launch_field_relax(nsfs_planner* h) {
+// Phase 3 (repeatable): relax every pending tile whose key is <= cap until none is left; nothing is relaxed beyond cap
+// (cap = +inf: to the fixed point).  Leaves the smallest key still pending in counts[6].
+int launch_field_relax(nsfs_planner* h, float cap) {
     FieldWork& f = h->field;
     FieldParams p = field_params(h);
+    if (cap < 3.0e38f) { const float c = cap > 0.f ? cap : 0.f; memcpy(&p.cap, &c, sizeof(c)); }   // non-negative floats order like their bits
+    field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 0);
+    h->launches++;
 #if NSFS_FIELD_PROF
     static unsigned long long* d_prof = nullptr;
     if (!d_prof) cudaMalloc(&d_prof, 8 * 4100);
@@ -627,7 +660,8 @@ int launch_field_relax(nsfs_planner* h) {
     NSFS_CUDA_TRY(h, cudaLaunchCooperativeKernel(async_tiles ? (void*)field_solve_async_kernel : (void*)field_solve_kernel, dim3(grid),
                                                  dim3(FIELD_THREADS), args, 0, h->stream));
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
-    h->launches++;
+    field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);
+    h->launches += 2;
 #if NSFS_FIELD_PROF
     { static unsigned long long hp[4100]; cudaMemcpyAsync(hp, p.prof, 8 * 4100, cudaMemcpyDeviceToHost, h->stream); cudaStreamSynchronize(h->stream);
       unsigned long long summax = 0; int nr = 0; for (int r = 0; r < 4000; ++r) { summax += hp[16 + r]; if (hp[16 + r]) nr = r + 1; }
@@ -636,6 +670,14 @@ int launch_field_relax(nsfs_planner* h) {
       fprintf(stderr, "[field prof] grid %d: per-block avg cycles: kernel %.0f relax %.0f | tile sums: load %.0f sweeps %.0f tail %.0f (cycles, summed over visits) | sub-block iterations %llu\n",
               grid, (double)hp[4] / grid, (double)hp[5] / grid, (double)hp[0], (double)hp[1], (double)hp[2], hp[3]); }
 #endif
+    return NSFS_OK;
+}
+
+int launch_field_min_pending(nsfs_planner* h) {
+    FieldWork& f = h->field;
+    field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, 0u, f.counts, 1);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;
 }
 
@@ -655,7 +697,7 @@ int launch_field_finish(nsfs_planner* h) {
 int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st) {
     (void)st;
     int rc = launch_field_begin(h, si, sj);
-    if (rc == NSFS_OK) rc = launch_field_relax(h);
+    if (rc == NSFS_OK) rc = launch_field_relax(h, 3.4e38f);
     if (rc == NSFS_OK) rc = launch_field_finish(h);
     return rc;
 }

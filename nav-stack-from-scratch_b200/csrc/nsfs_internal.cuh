@@ -37,10 +37,11 @@ struct FieldWork {
     uint8_t*  pred = nullptr;      // [N]
     uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
     int*      list[2] = {nullptr, nullptr};
-    int*      counts = nullptr;    // [8]: 0/1 list lengths, 2 rounds, 3 tile visits, 4 error flag, 5 reached
+    int*      counts = nullptr;    // [8]: 0 list length, 1 pending (async), 2 rounds, 3 tile visits, 4 error flag, 5 reached, 6 min pending key, 7 thr
     int       tiles_x = 0, tiles_y = 0;
     int       src_i = -1, src_j = -1;
     bool      valid = false;       // solved and finished: nsfs_field_path may walk pred
+    float     min_pending = 0.f;   // smallest tile key left pending by the last relax (+inf = none)
     bool      begun = false;       // g holds a field in progress (nsfs_field_begin or a full solve ran)
 };
 
@@ -109,8 +110,9 @@ void field_free(nsfs_planner* h);
 int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
 int launch_field_begin(nsfs_planner* h, int si, int sj);
 int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved);
-int launch_field_relax(nsfs_planner* h);
+int launch_field_relax(nsfs_planner* h, float cap);
 int launch_field_finish(nsfs_planner* h);
+int launch_field_min_pending(nsfs_planner* h);
 int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap, int* d_n, double* d_cost, int* d_status);
 
 int search_alloc(nsfs_planner* h, int want_slots);

@@ -64,6 +64,8 @@ def lib():
         L.nsfs_field_begin.argtypes = [vp, i32, i32]
         L.nsfs_field_inject_rows.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
         L.nsfs_field_relax.argtypes = [vp, C.POINTER(Stats)]
+        L.nsfs_field_relax_until.argtypes = [vp, C.c_float, C.POINTER(C.c_float), C.POINTER(Stats)]
+        L.nsfs_field_min_pending.argtypes = [vp, C.POINTER(C.c_float)]
         L.nsfs_field_finish.argtypes = [vp, C.POINTER(Stats)]
         L.nsfs_field_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.nsfs_field_path.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(dbl)]
@@ -207,11 +209,17 @@ class Planner:
         self._check(self.L.nsfs_field_inject_rows(self.h, int(row0), int(nrows), C.c_void_p(d_vals_ptr), C.byref(n)))
         return n.value
 
-    def field_relax(self):
-        st = Stats()
-        rc = self.L.nsfs_field_relax(self.h, C.byref(st))
+    def field_relax(self, cap=None):
+        """Relax to the local fixed point, or (cap given) only up to that cost; min_pending = smallest value left pending."""
+        st, mp = Stats(), C.c_float(0)
+        rc = self.L.nsfs_field_relax_until(self.h, C.c_float(3.4e38 if cap is None else float(cap)), C.byref(mp), C.byref(st))
         self._check(rc, allow=(E_RANGE,))
-        return dict(status=rc, stats=st.asdict())
+        return dict(status=rc, min_pending=mp.value, stats=st.asdict())
+
+    def field_min_pending(self):
+        mp = C.c_float(0)
+        self._check(self.L.nsfs_field_min_pending(self.h, C.byref(mp)))
+        return mp.value
 
     def field_finish(self):
         st = Stats()

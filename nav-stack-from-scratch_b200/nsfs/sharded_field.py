@@ -7,19 +7,24 @@ costs of a ghost-row cell depend on which of ITS neighbours are passable (astar.
 so each shard holds **4 extra rows of map** per side; the outer 2 take no in-edges (``active`` window) and exist only so
 that the ghost rows' edge masks equal the ones a monolithic solve would build.
 
-Per solve (bulk-synchronous between shards; inside a shard the local solver runs to its fixed point):
+Per solve, all shards advance together band by band (a delta-stepping loop ACROSS GPUs; inside a shard the solver's
+own tile scheduler runs to the band's local fixed point):
 
-    begin (source on its owner)  ->  relax
-    repeat:  send my first / last 2 OWNED rows to the upper / lower neighbour   (2*W floats each way)
+    begin (the source is seeded on its owner)
+    repeat:  send my first / last 2 OWNED rows to the upper / lower neighbour        (2*W floats each way)
              inject what arrived into my ghost rows: g = min(g, received)
-             all-reduce(sum) the number of cells that improved; stop at 0;  relax where something improved
+             M = all-reduce(min) of every shard's smallest pending value; stop when nothing is pending anywhere
+             relax every pending tile up to the cost cap M + band                     (shards with nothing below the cap skip)
     finish (predecessors, reached count over the owned rows)
 
-The exchange is the path's only collective: point-to-point rows + one scalar all-reduce per round.  Relaxation is
-monotone and the fp32 fixed point is unique (every value is the min over in-edges of fl(g[u] + w)), so the assembled
-result is bit-identical to the single-GPU field.
+With band = +inf this degenerates to "each shard to its fixed point, then exchange": correct, but a wave that starts
+in one shard is then solved shard after shard.  A finite band keeps every shard that the wavefront currently crosses
+busy in the same round.  The exchange is the path's only collective: point-to-point rows + one scalar all-reduce per
+round.  Relaxation is monotone and the fp32 fixed point is unique (every value is the min over in-edges of
+fl(g[u] + w)), so the assembled result is bit-identical to the single-GPU field whatever the band.
 
-``solver`` objects implement: begin(src|None), inject(row0, rows)->improved, relax(), finish()->dict, rows(row0, n),
+``solver`` objects implement: begin(src|None), inject(row0, rows)->improved, relax(cap|None), min_pending()->float,
+finish()->dict, rows(row0, n),
 where ``rows`` are 2-D arrays/tensors [n, W] in the solver's own memory space (torch CUDA tensors for the GPU solver).
 This module contains no search code: the GPU solver is nsfs.capi.Planner; tests plug a CPU checker in to exercise the
 partition / exchange / termination logic under gloo.
@@ -81,9 +86,6 @@ class FieldShard:
     def start(self, src):
         mine = src is not None and self.r0 <= src[0] < self.r1
         self.solver.begin((src[0] - self.lo, src[1]) if mine else None)
-        if mine:
-            self.solver.relax()
-            self.relaxes += 1
 
     def boundary_rows(self):
         """(rows for the upper neighbour, rows for the lower neighbour): my first / last GHOST owned rows."""
@@ -100,9 +102,12 @@ class FieldShard:
             improved += self.solver.inject(self.loc(self.r1), from_down)
         return improved
 
-    def relax(self):
-        self.solver.relax()
+    def relax(self, cap=None):
+        self.solver.relax(cap)
         self.relaxes += 1
+
+    def min_pending(self):
+        return self.solver.min_pending()
 
     def finish(self):
         return self.solver.finish()
@@ -112,24 +117,34 @@ class FieldShard:
 
 
 # ---- drivers --------------------------------------------------------------------------------------------------
-def solve_in_process(shards, src, max_rounds=100000):
+INF = float("inf")
+DEFAULT_BAND = 2048.0      # cost units a round may advance; see the module docstring
+
+
+def _cap(m, band):
+    return None if band is None or band == INF else m + band
+
+
+def solve_in_process(shards, src, band=DEFAULT_BAND, max_rounds=1000000):
     """All shards live in this process (one GPU or a CPU test): lockstep rounds, neighbours read directly."""
     for s in shards:
         s.start(src)
     rounds = 0
     while rounds < max_rounds:
         rows = [s.boundary_rows() for s in shards]
-        improved = []
         for k, s in enumerate(shards):
             from_up = rows[k - 1][1] if k > 0 else None
             from_down = rows[k + 1][0] if k + 1 < len(shards) else None
-            improved.append(s.absorb(_snapshot(from_up), _snapshot(from_down)))
-        rounds += 1
-        if sum(improved) == 0:
+            s.absorb(_snapshot(from_up), _snapshot(from_down))
+        pend = [s.min_pending() for s in shards]
+        m = min(pend)
+        if not m < INF:
             break
-        for s, n in zip(shards, improved):
-            if n:
-                s.relax()
+        rounds += 1
+        cap = _cap(m, band)
+        for s, p in zip(shards, pend):
+            if p < INF and (cap is None or p <= cap):
+                s.relax(cap)
     return dict(rounds=rounds, results=[s.finish() for s in shards])
 
 
@@ -139,17 +154,18 @@ def _snapshot(x):
     return x.clone() if hasattr(x, "clone") else np.array(x, copy=True)
 
 
-def solve_distributed(shard: FieldShard, src, dist, device=None, max_rounds=100000):
+def solve_distributed(shard: FieldShard, src, dist, device=None, band=DEFAULT_BAND, max_rounds=1000000):
     """One shard per process (torch.distributed: NCCL on GPUs, gloo in the CPU tests)."""
     import torch
 
-    rank, world, W = shard.rank, shard.part.world, shard.part.W
+    rank, world = shard.rank, shard.part.world
+    on_cuda = device is not None and device.type == "cuda"
     shard.start(src)
     rounds = 0
+    as_t = (lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
     while rounds < max_rounds:
         up, down = shard.boundary_rows()
         ops, recv_up, recv_down, keep = [], None, None, []
-        as_t = (lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
         if rank > 0:
             t = as_t(up).contiguous(); keep.append(t)
             recv_up = torch.empty_like(t)
@@ -161,16 +177,19 @@ def solve_distributed(shard: FieldShard, src, dist, device=None, max_rounds=1000
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        if device is not None and device.type == "cuda":
+        if on_cuda:
             torch.cuda.current_stream(device).synchronize()
-        improved = shard.absorb(recv_up, recv_down)
-        flag = torch.tensor([improved], dtype=torch.int64, device=device if device is not None else "cpu")
-        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
-        rounds += 1
-        if int(flag.item()) == 0:
+        shard.absorb(recv_up, recv_down)
+        pend = shard.min_pending()
+        flag = torch.tensor([pend if pend < INF else 3.0e38], dtype=torch.float32, device=device if device is not None else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        m = float(flag.item())
+        if m >= 3.0e38:
             break
-        if improved:
-            shard.relax()
+        rounds += 1
+        cap = _cap(m, band)
+        if pend < INF and (cap is None or pend <= cap):
+            shard.relax(cap)
     return dict(rounds=rounds, result=shard.finish())
 
 
@@ -198,6 +217,7 @@ class GpuShardSolver:
         self.P.set_map(infl_rows, lo_rows, lo_thresh)
         self._g = None
         self.stats = []
+        self.status = 0
 
     def _gview(self):
         if self._g is None:
@@ -208,6 +228,7 @@ class GpuShardSolver:
     def begin(self, src):
         self.P.field_begin(src)
         self._g = None
+        self.status = 0
 
     def inject(self, row0, rows):
         t = rows if isinstance(rows, self.torch.Tensor) else self.torch.from_numpy(np.ascontiguousarray(rows, np.float32))
@@ -215,13 +236,19 @@ class GpuShardSolver:
         self.torch.cuda.current_stream(self.dev).synchronize()      # the nsfs handle launches on its own stream
         return self.P.field_inject_rows(row0, t.shape[0], t.data_ptr())
 
-    def relax(self):
-        r = self.P.field_relax()
+    def relax(self, cap=None):
+        r = self.P.field_relax(cap)
         self.stats.append(r["stats"])
+        self.status = self.status or r["status"]
         return r
 
+    def min_pending(self):
+        return self.P.field_min_pending()
+
     def finish(self):
-        return self.P.field_finish()
+        r = self.P.field_finish()
+        r["status"] = r["status"] or self.status
+        return r
 
     def rows(self, row0, n):
         return self._gview()[row0:row0 + n]

@@ -490,8 +490,9 @@ out:
  * in/out, every finite cell is a source, and cells outside rows [row_lo, row_hi) take no in-edges (they exist only so
  * that their neighbours' direction costs see the true neighbourhood).  slack = the relaxation slack (the reference uses
  * 1e-5, astar.cpp:116; 0 makes the fixed point unique so sharded and monolithic solves can be compared bit for bit).
+ * cap: candidates above it are not applied (the multi-GPU driver advances all shards band by band).
  * Returns the number of label improvements, or a negative NSO_E_* code. */
-long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack) {
+long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack, double cap) {
     const int H = m->H, W = m->W;
     const long long N = (long long)H * W;
     int32_t* fifo = (int32_t*)malloc((size_t)N * sizeof(int32_t));
@@ -516,6 +517,7 @@ long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int ro
             double cand = g[ku] + (card ? 1 : M_SQRT2);
             card = !card;
             if (vi < row_lo || vi >= row_hi) continue;
+            if (cand > cap) continue;              /* beyond the band: stays pending (see nso_field_min_pending) */
             if (g[kv] > cand + slack) {
                 g[kv] = cand; improved++;
                 if (!inq[kv]) { fifo[(head + cnt) % N] = (int32_t)kv; cnt++; inq[kv] = 1; }
@@ -527,3 +529,26 @@ out:
     return status < 0 ? status : improved;
 }
 
+/* Smallest candidate that would still improve a label of the shard (1e300 when it is at its fixed point): what a capped
+ * nso_field_relax_window left pending. */
+double nso_field_min_pending(const nso_map* m, const double* g, int row_lo, int row_hi, double slack) {
+    const int H = m->H, W = m->W;
+    double best = 1e300;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const long long ku = (long long)i * W + j;
+            if (!(g[ku] < G_INF)) continue;
+            int card = 1;
+            for (int d = 0; d < 8; ++d) {
+                int t = nso_test_pos(m, i + DI[d], j + DJ[d]);
+                if (t == NSO_E_RANGE || !t) continue;
+                long long kv = ku + (long long)DI[d] * W + DJ[d];
+                int vi = (int)(kv / W);
+                double cand = g[ku] + (card ? 1 : M_SQRT2);
+                card = !card;
+                if (vi < row_lo || vi >= row_hi) continue;
+                if (g[kv] > cand + slack && cand < best) best = cand;
+            }
+        }
+    return best;
+}

@@ -57,7 +57,8 @@ int nso_heap_trace(int mode, int n_ops, const int32_t* ops, int32_t* out);
 int nso_field_fixed_point(const nso_map* m, int si, int sj, double* g);
 
 /* One shard of a row-partitioned field: warm start from g, rows outside [row_lo,row_hi) take no in-edges. */
-long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack);
+long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack, double cap);
+double nso_field_min_pending(const nso_map* m, const double* g, int row_lo, int row_hi, double slack);
 
 #ifdef __cplusplus
 }

@@ -106,13 +106,20 @@ class Oracle:
                                             g.ctypes.data_as(C.c_void_p))
         return rc, g.reshape(self.H, self.W)
 
-    def field_relax_window(self, g, row_lo=0, row_hi=None, slack=0.0):
-        """Warm-started label-correcting relaxation of one row-block shard (g is float64 [H, W], updated in place)."""
+    def field_relax_window(self, g, row_lo=0, row_hi=None, slack=0.0, cap=1e300):
+        """Warm-started label-correcting relaxation of one row-block shard (g is float64 [H, W], updated in place);
+        candidates above ``cap`` are left pending."""
         assert g.dtype == np.float64 and g.flags.c_contiguous and g.shape == (self.H, self.W)
         self.lib.nso_field_relax_window.restype = C.c_longlong
-        self.lib.nso_field_relax_window.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double]
+        self.lib.nso_field_relax_window.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         return self.lib.nso_field_relax_window(C.addressof(self.map), g.ctypes.data_as(C.c_void_p), int(row_lo),
-                                               int(self.H if row_hi is None else row_hi), float(slack))
+                                               int(self.H if row_hi is None else row_hi), float(slack), float(cap))
+
+    def field_min_pending(self, g, row_lo=0, row_hi=None, slack=0.0):
+        self.lib.nso_field_min_pending.restype = C.c_double
+        self.lib.nso_field_min_pending.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double]
+        return self.lib.nso_field_min_pending(C.addressof(self.map), g.ctypes.data_as(C.c_void_p), int(row_lo),
+                                              int(self.H if row_hi is None else row_hi), float(slack))
 
     def find_better_point(self, bad):
         fi, fj = C.c_int(0), C.c_int(0)

@@ -24,7 +24,7 @@ def main():
         src = mapgen.sample_free_cells(infl, lo, 1, 41)[0]
         part = sf.RowPartition(90, 70, world)
         shard = sf.FieldShard(part, rank, OracleShardSolver(orc, part, rank, infl, lo))
-        out = sf.solve_distributed(shard, src, dist)
+        out = sf.solve_distributed(shard, src, dist, band=25.0)
         parts = [None] * world
         dist.all_gather_object(parts, (np.array(shard.owned_rows()), out["result"]["reached"], out["rounds"]))
         if rank == 0:

@@ -31,10 +31,14 @@ class OracleShardSolver:
         cur[better] = rows[better]
         return int(better.sum())
 
-    def relax(self):
-        rc = self.O.field_relax_window(self.g, self.a0, self.a1, 0.0)
+    def relax(self, cap=None):
+        rc = self.O.field_relax_window(self.g, self.a0, self.a1, 0.0, 1e300 if cap is None else cap)
         if rc < 0:
             self.status = int(rc)
+
+    def min_pending(self):
+        m = self.O.field_min_pending(self.g, self.a0, self.a1, 0.0)
+        return m if m < 1e299 else float("inf")
 
     def finish(self):
         return dict(status=self.status, reached=int((self.g[self.r0:self.r1] < INF).sum()))
@@ -52,5 +56,5 @@ def monolithic(oracle_mod, infl, lo, src):
     O = oracle_mod.Oracle(infl, lo)
     g = np.full(infl.shape, INF, np.float64)
     g[src[0], src[1]] = 0.0
-    rc = O.field_relax_window(g, 0, infl.shape[0], 0.0)
+    rc = O.field_relax_window(g, 0, infl.shape[0], 0.0, 1e300)
     return rc, g

@@ -33,8 +33,9 @@ def test_query_slices_cover_the_batch_once():
 
 @pytest.mark.parametrize("spec", [(96, 64, 0.12, 31, True), (61, 47, 0.25, 32, True), (40, 23, 0.10, 33, False)],
                          ids=["framed", "dense", "unframed-wrap"])
-@pytest.mark.parametrize("world", [1, 2, 3, 5])
-def test_sharded_field_equals_monolithic(oracle_mod, spec, world):
+@pytest.mark.parametrize("world,band", [(1, None), (2, None), (3, None), (5, None), (2, 12.5), (3, 40.0)],
+                         ids=["1", "2", "3", "5", "2-band12.5", "3-band40"])
+def test_sharded_field_equals_monolithic(oracle_mod, spec, world, band):
     H, W, p, seed, frame = spec
     infl, lo = mapgen.synth_map(H, W, p, seed, False, frame)
     if not frame:
@@ -46,7 +47,7 @@ def test_sharded_field_equals_monolithic(oracle_mod, spec, world):
     src = mapgen.sample_free_cells(infl, lo, 1, seed)[0]
     rc, want = monolithic(oracle_mod, infl, lo, src)
     part, shards = make_oracle_shards(oracle_mod, infl, lo, world)
-    out = sf.solve_in_process(shards, src)
+    out = sf.solve_in_process(shards, src, band=band)
     statuses = [r["status"] for r in out["results"]]
     assert rc >= 0 and all(s == 0 for s in statuses)
     got = np.concatenate([s.owned_rows() for s in shards])
