@@ -610,7 +610,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=16384, help="queries per step per GPU (c4); keep it >= 3x the 4736 query slots")
+    ap.add_argument("--batch", type=int, default=28416, help="queries per step per GPU (c4): two waves of the 14 208 query slots (24 warps x 4 teams x 148 SMs)")
     ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -109,6 +109,7 @@ void nsfs_destroy(nsfs_t* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     field_free(h);
     search_free(h);
+    team_free(h);
     cudaFree(h->d_infl); cudaFree(h->d_lo); cudaFree(h->d_free); cudaFree(h->d_inflated);
     cudaFree(h->d_out_mask); cudaFree(h->d_in_mask); cudaFree(h->d_scratch);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -191,6 +192,25 @@ static void fill_stats(nsfs_stats* st, const long long* s5, long long launches, 
     st->launches = launches; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
 }
 
+// Batches of Astar / Djikstra go to the four-queries-per-warp kernel (search_team.cu); single queries, ThetaStar, the
+// fallback search and degenerate widths stay on the one-query-per-warp kernel (search.cu).
+static bool use_team_kernel(const nsfs_planner* h, int kind, int algo, int nq) {
+    if (kind != 0 || (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA) || h->W < 3) return false;
+    if (h->opt_search_kernel == 1) return false;
+    if (h->opt_search_kernel == 2) return true;
+    return nq >= 2;
+}
+
+static int launch_any_search(nsfs_planner* h, bool team, int kind, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,
+                             double* d_g_goal, int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_s5) {
+    if (team) {
+        if (h->search.slots > 1) search_free(h);          // the two kernels' per-query state competes for the same HBM
+        return launch_search_team(h, algo, mode, nq, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5);
+    }
+    if (nq > 1 && h->team.slots > 0) team_free(h);
+    return launch_search(h, kind, algo, mode, nq, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5);
+}
+
 // Runs nq queries given as host arrays; kind 0 = plan, 1 = find_better_point.  Retries open-list overflows once
 // with the provable upper bound on the open-list length (every directed edge is relaxed at most once => 8N+1).
 static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* q_host,
@@ -211,11 +231,14 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     char* d = (char*)h->d_scratch;
     NSFS_CUDA_TRY(h, cudaMemcpyAsync(d + o_q, q_host, (size_t)nq * qw * 4, cudaMemcpyHostToDevice, h->stream));
     NSFS_CUDA_TRY(h, cudaMemsetAsync(d + o_s5, 0, 5 * 8, h->stream));
-    if ((rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    if (path_elems) NSFS_CUDA_TRY(h, cudaMemsetAsync(d + o_paths, 0, path_elems * 4, h->stream));   // cells beyond path_len read as 0
+    const bool team = use_team_kernel(h, kind, algo, nq);
+    if (!team && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    if (team && (rc = team_alloc(h, nq)) != NSFS_OK) return rc;
     Timer tm(h);
-    rc = launch_search(h, kind, algo, mode, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (double*)(d + o_g),
-                       (int32_t*)(d + o_len), (long long*)(d + o_set), path_elems ? (int32_t*)(d + o_paths) : nullptr, path_cap,
-                       (long long*)(d + o_s5));
+    rc = launch_any_search(h, team, kind, algo, mode, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (double*)(d + o_g),
+                           (int32_t*)(d + o_len), (long long*)(d + o_set), path_elems ? (int32_t*)(d + o_paths) : nullptr, path_cap,
+                           (long long*)(d + o_s5));
     if (rc != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
@@ -235,15 +258,15 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     long long worst = 8 * h->N + 16;
     if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;      // search_alloc clamps to 32-bit heap positions
     for (int q = 0; q < nq; ++q) {
-        if (stat_h[q] != NSFS_E_HEAP || h->search.heap_cap >= worst) continue;
-        const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots;
-        h->opt_heap_cap = worst; h->opt_max_slots = 1;
+        if (stat_h[q] != NSFS_E_HEAP || (!team && h->search.heap_cap >= worst)) continue;
+        const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots, keep_kernel = h->opt_search_kernel;
+        h->opt_heap_cap = worst; h->opt_max_slots = 1; h->opt_search_kernel = 1;
         search_free(h);
         int32_t s1 = 0; double g1 = 0; int32_t l1 = 0; long long e1 = 0;
         std::vector<int32_t> p1(paths ? (size_t)path_cap * 2 : (kind == 1 ? 2 : 0));
         rc = run_search_host(h, kind, algo, mode, 1, q_host + (size_t)q * qw, &s1, &g1, &l1, &e1, p1.empty() ? nullptr : p1.data(),
                              path_cap, nullptr);
-        h->opt_heap_cap = keep_cap; h->opt_max_slots = keep_slots;
+        h->opt_heap_cap = keep_cap; h->opt_max_slots = keep_slots; h->opt_search_kernel = keep_kernel;
         search_free(h);
         if (rc != NSFS_OK) return rc;
         if (status) status[q] = s1;
@@ -307,23 +330,45 @@ int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int
     if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
     if (!nq) return NSFS_OK;
     const long long launches0 = h->launches;
-    if ((rc = search_alloc(h, nq)) != NSFS_OK) return rc;
-    long long* d_s5 = nullptr;
-    if (st) {
-        if ((rc = ensure_scratch(h, 256)) != NSFS_OK) return rc;
-        d_s5 = (long long*)h->d_scratch;
-        NSFS_CUDA_TRY(h, cudaMemsetAsync(d_s5, 0, 5 * 8, h->stream));
-    }
+    const bool team = use_team_kernel(h, 0, algo, nq);
+    if (!team && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    if (team && (rc = team_alloc(h, nq)) != NSFS_OK) return rc;
+    if ((rc = ensure_scratch(h, 256)) != NSFS_OK) return rc;
+    long long* d_s5 = (long long*)h->d_scratch;
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(d_s5, 0, 5 * 8, h->stream));
     Timer tm(h);
-    rc = launch_search(h, 0, algo, cost_mode, nq, d_sg4, d_status, d_g_goal, d_path_len, d_settled, d_paths_ij, path_cap, d_s5);
+    rc = launch_any_search(h, team, 0, algo, cost_mode, nq, d_sg4, d_status, d_g_goal, d_path_len, d_settled, d_paths_ij, path_cap, d_s5);
     if (rc != NSFS_OK) return rc;
-    if (st) {
-        const float ms = tm.stop_sync();
-        long long s5[5];
-        NSFS_CUDA_TRY(h, cudaMemcpy(s5, d_s5, sizeof(s5), cudaMemcpyDeviceToHost));
-        fill_stats(st, s5, h->launches - launches0, ms, tm.main_kernel_ms());
+    const float ms = tm.stop_sync();
+    const float main_ms = tm.main_kernel_ms();
+    long long s5[5];
+    NSFS_CUDA_TRY(h, cudaMemcpy(s5, d_s5, sizeof(s5), cudaMemcpyDeviceToHost));
+    fill_stats(st, s5, h->launches - launches0, ms, main_ms);
+    if (team && d_status) {
+        // queries the batch kernel could not finish exactly (open list beyond its slot, 16-bit step counts): re-run each on
+        // the wide kernel with the worst-case capacity, results written into the same device arrays
+        std::vector<int32_t> stat_h(nq);
+        NSFS_CUDA_TRY(h, cudaMemcpy(stat_h.data(), d_status, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        long long worst = 8 * h->N + 16;
+        if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;
+        bool any = false;
+        for (int q = 0; q < nq; ++q) any = any || stat_h[q] == NSFS_E_HEAP;
+        if (any) {
+            const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots;
+            h->opt_heap_cap = worst; h->opt_max_slots = 1;
+            search_free(h);
+            for (int q = 0; q < nq && rc == NSFS_OK; ++q) {
+                if (stat_h[q] != NSFS_E_HEAP) continue;
+                rc = launch_search(h, 0, algo, cost_mode, 1, d_sg4 + 4 * (size_t)q, d_status + q, d_g_goal ? d_g_goal + q : nullptr,
+                                   d_path_len ? d_path_len + q : nullptr, d_settled ? d_settled + q : nullptr,
+                                   d_paths_ij ? d_paths_ij + (size_t)q * path_cap * 2 : nullptr, path_cap, nullptr);
+            }
+            if (rc == NSFS_OK) NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            h->opt_heap_cap = keep_cap; h->opt_max_slots = keep_slots;
+            search_free(h);
+        }
     }
-    return NSFS_OK;
+    return rc;
 }
 
 int nsfs_find_better_point_batch(nsfs_t* h, int n, const int32_t* bad_ij, int32_t* out_ij, int32_t* status, nsfs_stats* st) {
@@ -542,8 +587,10 @@ void* nsfs_stream(nsfs_t* h) { return h ? (void*)h->stream : nullptr; }
 
 int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!h || !key) return NSFS_E_ARG;
-    if (!strcmp(key, "max_slots")) { h->opt_max_slots = value; search_free(h); return NSFS_OK; }
+    if (!strcmp(key, "max_slots")) { h->opt_max_slots = value; search_free(h); team_free(h); return NSFS_OK; }
     if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
+    if (!strcmp(key, "team_heap_cap")) { h->opt_team_heap_cap = value; team_free(h); return NSFS_OK; }
+    if (!strcmp(key, "search_kernel")) { h->opt_search_kernel = value; return NSFS_OK; }
     if (!strcmp(key, "field_inner")) { h->opt_field_inner = value; return NSFS_OK; }
     if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }

@@ -55,6 +55,16 @@ struct SearchWork {
     int*      work_counter = nullptr;
 };
 
+struct TeamWork {
+    // batch kernel (search_team.cu): one slot per team of 8 lanes, four teams per warp
+    int       slots = 0;
+    long long heap_cap = 0;
+    uint2*    cells = nullptr;     // [slots][N]   {n_card | n_diag << 16, epoch << 4 | visited << 3 | parent direction}
+    unsigned long long* heap = nullptr;
+    uint32_t* epoch = nullptr;
+    int*      work_counter = nullptr;
+};
+
 }  // namespace nsfs
 
 struct nsfs_planner {
@@ -78,6 +88,7 @@ struct nsfs_planner {
 
     nsfs::FieldWork field;
     nsfs::SearchWork search;
+    nsfs::TeamWork team;
 
     // small device scratch + pinned host mirror for per-call scalars/results
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -86,6 +97,8 @@ struct nsfs_planner {
     long long launches = 0;
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
+    long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
+    long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
     long long opt_field_inner = 0;      // 0 = default (4)
     long long opt_field_delta = 0;      // 0 = default (64)
     long long opt_field_mode = 0;       // 0 = asynchronous tile scheduling, 1 = bulk-synchronous rounds
@@ -121,6 +134,11 @@ void search_free(nsfs_planner* h);
 int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* d_q,
                   int32_t* d_status, double* d_g_goal, int32_t* d_path_len, long long* d_settled,
                   int32_t* d_paths, int path_cap, long long* d_stats5);
+
+int team_alloc(nsfs_planner* h, int want_slots);
+void team_free(nsfs_planner* h);
+int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status, double* d_g_goal,
+                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5);
 
 int launch_los_batch(nsfs_planner* h, int n, const int32_t* d_seg4, int8_t* d_out);
 int launch_any_angle(nsfs_planner* h, int n, const int32_t* d_pts, uint8_t* d_keep);

@@ -1,0 +1,388 @@
+// Exact-order Astar / Djikstra plan() for BATCHES: four queries per warp, eight lanes ("a team") per query.
+//
+// Why a second kernel: ncu on the one-query-per-warp kernel (search.cu) at batch size shows it is bound by issue slots,
+// not by memory: ~500 warp instructions per pop, most of them warp-uniform bookkeeping that all 32 lanes repeat
+// (profiles/r01_search_ncu.md).  Here one instruction stream serves four queries: every lane group of 8 runs its own
+// query in lockstep with the other three, so the same bookkeeping instructions advance four open lists at once.
+// Eight lanes are also exactly the 8 neighbours of an expansion.
+//
+// What is replayed is unchanged (see search.cu): libstdc++'s push_heap / pop_heap on 64-bit entries f:18 | g:17 | key:29
+// with the reference's three comparators, int-truncated keys, pushes in NB_LUT order, closed cells re-labelled.
+//   pop   3-level chunks: team lane t < 7 owns internal node t of the subtree under the hole and loads both children
+//         with one 128-bit load; two ballots give the path through the three levels; stop at the first picked child that
+//         sorts after the displaced element (same final array as sink-to-leaf + sift-up, priorities are monotone on a path)
+//   push  lanes 1..7 load ancestors 1..7 of the new leaf, one ballot finds how far the element rises
+// Per-cell record, 8 bytes instead of 16 so that four times as many searches fit in HBM:
+//   x = n_card | n_diag << 16     g = n_card + n_diag * sqrt(2): the label as EXACT step counts (SURVEY.md §7 "hard parts" 6)
+//   y = epoch << 4 | visited << 3 | direction of the edge from the parent (parent key = key - OFF[d])
+// Every decision the reference takes on g is reproduced from the integer pair: (int)g and (int)(g + h) cannot differ because
+// a + b*sqrt(2) with b != 0 stays >= 1/(2.83 b) away from any integer (b < 65536 here) while fp64 accumulates < 1e-9 of
+// error, and "g[v] > cand + 1e-5" compares two such numbers whose difference is either exactly 0 or >= 1e-5-clear for
+// b < 35000.  g(goal) is reported as n_card + n_diag*sqrt(2) in fp64: within 1e-12 relative of the reference's running
+// sum (the stated bar is 1e-5).  A label that would overflow 16 bits ends the query with NSFS_E_HEAP, which the caller
+// re-runs on the wide kernel of search.cu, like an open list that outgrows its slot.
+#include "nsfs_internal.cuh"
+
+namespace nsfs {
+
+constexpr int kKeyBitsT = 29, kGBitsT = 17;
+constexpr unsigned long long kKeyMaskT = (1ull << kKeyBitsT) - 1ull;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TEAM_WARPS_PER_BLOCK = 4;
+enum { PH_FETCH = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINAL = 3, PH_DONE = 4 };
+
+struct TeamParams {
+    const uint16_t* out_mask;
+    uint2* cells;                 // [slots][N]
+    unsigned long long* heap;     // [slots][heap_stride]
+    uint32_t* epoch;              // [slots]
+    int* work_counter;
+    int H, W;
+    long long N;
+    long long heap_cap, heap_stride;
+    int slots;
+    int mode;
+    int nq;
+    const int32_t* q;             // {si, sj, gi, gj} per query
+    int32_t* status;
+    double* g_goal;
+    int32_t* path_len;
+    long long* settled;
+    int32_t* paths;               // optional [nq][path_cap][2]
+    int path_cap;
+    long long* stats5;
+};
+
+struct PrioT {
+    int sh;
+    unsigned long long msk;
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long e) const { return (e >> sh) & msk; }
+};
+
+__device__ __forceinline__ unsigned team_ballot(bool pred, int tbase) { return (__ballot_sync(FULL, pred) >> tbase) & 0xffu; }
+
+// std::pop_heap for every team with act set (each on its own array); warp-uniform control flow.
+__device__ __forceinline__ void team_pop(unsigned long long* a, uint32_t& n, bool act, const PrioT prio, int tl, int tbase, int r, uint32_t o) {
+    uint32_t len = 0;
+    unsigned long long v = 0, pv = 0;
+    bool sinking = false;
+    if (act) {
+        len = n - 1u;
+        n = len;
+        if (len > 0u) { v = a[len + 1u]; pv = prio(v); sinking = true; }
+    }
+    uint32_t c1 = 1u;                                     // position (heap index + 1) of the hole
+    while (__any_sync(FULL, sinking)) {
+        const uint32_t pos = (c1 << r) + o;               // my node; its children sit at positions 2*pos, 2*pos + 1
+        const uint32_t lpos = 2u * pos;
+        const bool has = sinking && tl < 7 && (c1 >> (30 - r)) == 0u && lpos <= len;
+        ulonglong2 ch = make_ulonglong2(0ull, 0ull);
+        if (has) ch = *reinterpret_cast<const ulonglong2*>(a + lpos);
+        const bool left = !(lpos + 1u <= len) || prio(ch.y) > prio(ch.x);      // right child unless it sorts after the left one
+        const unsigned long long pick = left ? ch.x : ch.y;
+        const bool stop = !has || prio(pick) > pv;
+        const unsigned m_left = team_ballot(left, tbase);
+        const unsigned m_stop = team_ballot(stop, tbase);
+        uint32_t node = 0, steps = 0, path = 0;
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            if ((m_stop >> node) & 1u) break;
+            path |= 1u << node;
+            node = 2u * node + 2u - ((m_left >> node) & 1u);
+            ++steps;
+        }
+        if (sinking && ((path >> tl) & 1u)) a[pos] = pick;
+        const int rq = 31 - __clz(node + 1u);
+        const uint32_t npos = (c1 << rq) + (node + 1u - (1u << rq));
+        if (sinking) {
+            if (steps < 3u) { if (tl == 0) a[npos] = v; sinking = false; }
+            else c1 = npos;
+        }
+        __syncwarp();
+    }
+}
+
+// std::push_heap for every team with pushing set.
+__device__ __forceinline__ void team_push(unsigned long long* a, uint32_t& n, unsigned long long v, bool pushing, const PrioT prio, int tl, int tbase) {
+    uint32_t base = n + 1u;                               // position of the hole the new element rises from
+    const unsigned long long pv = prio(v);
+    bool rising = pushing;
+    while (__any_sync(FULL, rising)) {
+        const uint32_t q = base >> tl;                    // tl >= 1: position of the tl-th ancestor of the hole
+        const bool valid = rising && tl >= 1 && q >= 1u;
+        unsigned long long e = 0;
+        if (valid) e = a[q];
+        const unsigned rise = team_ballot(valid && prio(e) > pv, tbase);
+        const int m = __ffs(~(rise >> 1)) - 1;            // run of ancestors (from the parent up) that sort after v: 0..7
+        if (rising && tl >= 1 && tl <= m) a[base >> (tl - 1)] = e;
+        if (rising) {
+            if (m < 7) { if (tl == 0) a[base >> m] = v; rising = false; }
+            else base >>= 7;                              // seven levels up and still rising
+        }
+        __syncwarp();
+    }
+    if (pushing) n = n + 1u;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(TeamParams p) {
+    const int lane = threadIdx.x & 31, tl = lane & 7, tbase = lane & 24;
+    const int slot = (blockIdx.x * TEAM_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const int W = p.W, mode = p.mode;
+    const uint32_t uW = (uint32_t)W, uN = (uint32_t)p.N;
+    const bool have_slot = slot < p.slots;
+    uint2* cells = p.cells + (size_t)(have_slot ? slot : 0) * (size_t)p.N;
+    unsigned long long* heap = p.heap + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
+    PrioT prio;
+    if (mode == NSFS_MODE_F) { prio.sh = kKeyBitsT + kGBitsT; prio.msk = ~0ull; }
+    else if (mode == NSFS_MODE_G) { prio.sh = kKeyBitsT; prio.msk = (1ull << kGBitsT) - 1ull; }
+    else { prio.sh = kKeyBitsT; prio.msk = ~0ull; }
+    const int nr = 31 - __clz(tl + 1);                    // my node of a 3-level subtree: level 0,1,1,2,2,2,2 (lane 7: unused)
+    const uint32_t no = (uint32_t)(tl + 1) - (1u << nr);
+    const int my_di = nb_di(tl), my_dj = nb_dj(tl);
+    const int my_off = my_di * W + my_dj;
+
+    uint32_t epoch = have_slot ? p.epoch[slot] : 0u;
+    int phase = have_slot ? PH_FETCH : PH_DONE;
+    // per-query state (uniform within a team)
+    uint32_t n = 0, ks = 0, kg = 0xffffffffu, peak = 0, wk = 0;
+    int qi = 0, gi = 0, gj = 0, status = NSFS_OK, plen = 0;
+    bool found = false;
+    long long pops = 0, expansions = 0, pushes = 0;
+
+    for (;;) {
+        // ---- next query -----------------------------------------------------------------------------------------
+        {
+            const bool fetch = phase == PH_FETCH;
+            int q = 0;
+            if (fetch && tl == 0) q = atomicAdd(p.work_counter, 1);
+            q = __shfl_sync(FULL, q, 0, 8);
+            if (fetch) {
+                if (q >= p.nq) phase = PH_DONE;
+                else {
+                    qi = q;
+                    ++epoch;
+                    const int si = p.q[4 * qi], sj = p.q[4 * qi + 1];
+                    gi = p.q[4 * qi + 2]; gj = p.q[4 * qi + 3];
+                    n = 0; peak = 0; pops = 0; expansions = 0; pushes = 0; found = false; status = NSFS_OK; plen = 1;
+                    kg = (gi >= 0 && gi < p.H && gj >= 0 && gj < W) ? (uint32_t)(gi * W + gj) : 0xffffffffu;
+                    if (si < 0 || si >= p.H || sj < 0 || sj >= W) { status = NSFS_E_ARG; ks = 0; phase = PH_FINAL; }
+                    else {
+                        ks = (uint32_t)(si * W + sj);
+                        // start cell: g = 0, then the first push into an empty list is a plain store (astar.cpp:45-52)
+                        double h0 = 0.0;
+                        if (ALGO == NSFS_ASTAR) {
+                            const int ax = abs(gi - si), ay = abs(gj - si);        // dist_oct's slip: both against the ROW (bot_utils.cpp:47)
+                            h0 = __dadd_rn(__dmul_rn((double)min(ax, ay), kSqrt2D), (double)abs(ax - ay));
+                        }
+                        const unsigned long long f0 = (mode == NSFS_MODE_G) ? 0ull : (unsigned long long)(unsigned)__double2int_rz(h0);
+                        if (tl == 0) {
+                            __stcg(cells + ks, make_uint2(0u, epoch << 4));
+                            heap[1] = (f0 << (kKeyBitsT + kGBitsT)) | (unsigned long long)ks;
+                        }
+                        n = 1; pushes = 1; peak = 1;
+                        phase = PH_SEARCH;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (__all_sync(FULL, phase == PH_DONE)) break;
+
+        // ---- one pop + expansion for every searching team ------------------------------------------------------------
+        {
+            const bool act = phase == PH_SEARCH;
+            unsigned long long top = 0;
+            if (act) top = heap[1];
+            const uint32_t ku = (uint32_t)(top & kKeyMaskT);
+            const int i = (int)(ku / uW), j = (int)(ku - (uint32_t)i * uW);
+            const uint32_t kv = ku + (uint32_t)my_off;               // my neighbour: flat key; its row follows the column wrap
+            int vi = i + my_di;
+            { const int vj = j + my_dj; if (vj >= W) vi++; else if (vj < 0) vi--; }
+            uint2 pre = make_uint2(0u, 0u), cu_l = make_uint2(0u, 0u);
+            uint32_t om_l = 0;
+            if (act) {
+                if (kv < uN) pre = __ldcg(cells + kv);
+                if (tl == 0) cu_l = __ldcg(cells + ku);
+                if (tl == 1) om_l = __ldg(p.out_mask + ku);
+            }
+            team_pop(heap, n, act, prio, tl, tbase, nr, no);
+            uint2 cu;
+            cu.x = __shfl_sync(FULL, cu_l.x, 0, 8); cu.y = __shfl_sync(FULL, cu_l.y, 0, 8);
+            const uint32_t om = __shfl_sync(FULL, om_l, 1, 8);
+            bool expand = act;
+            if (act) {
+                pops++;
+                if (cu.y & 8u) expand = false;                       // stale entry (astar.cpp:59-62)
+            }
+            if (expand) {
+                if (tl == 0) __stcg(&cells[ku].y, cu.y | 8u);
+                expansions++;
+                if (ku == kg) { found = true; expand = false; phase = PH_WALK; wk = kg; plen = 0; }        // astar.cpp:68
+                else if (om & kThrowBit) { status = NSFS_E_RANGE; expand = false; phase = PH_FINAL; }         // vector::at throws (R6)
+            }
+            // ---- my neighbour (astar.cpp:89-124) ----------------------------------------------------------------------
+            bool relax = false, overflow = false;
+            unsigned long long entry = 0;
+            if (expand && ((om >> tl) & 1u)) {
+                const bool valid = (pre.y >> 4) == epoch;
+                const bool diag = ((om >> (8 + tl)) & 1u) && tl;
+                const uint32_t nc = (cu.x & 0xffffu) + (diag ? 0u : 1u), nd = (cu.x >> 16) + (diag ? 1u : 0u);
+                const double cand = __dadd_rn((double)nc, __dmul_rn((double)nd, kSqrt2D));
+                const double gv = valid ? __dadd_rn((double)(pre.x & 0xffffu), __dmul_rn((double)(pre.x >> 16), kSqrt2D)) : kInfD;
+                relax = gv > __dadd_rn(cand, kSlack);                                                      // astar.cpp:116
+                if (relax) {
+                    if (nc > 0xffffu || nd > 0xffffu) { overflow = true; relax = false; }
+                    else {
+                        __stcg(cells + kv, make_uint2(nc | (nd << 16), (epoch << 4) | (valid ? (pre.y & 8u) : 0u) | (uint32_t)tl));
+                        double f = 0.0;
+                        if (mode != NSFS_MODE_G) {
+                            double h = 0.0;
+                            if (ALGO == NSFS_ASTAR) {
+                                const int ax = abs(gi - vi), ay = abs(gj - vi);
+                                h = __dadd_rn(__dmul_rn((double)min(ax, ay), kSqrt2D), (double)abs(ax - ay));
+                            }
+                            f = __dadd_rn(cand, h);
+                        }
+                        entry = ((unsigned long long)(unsigned)__double2int_rz(f) << (kKeyBitsT + kGBitsT)) |
+                                ((unsigned long long)(unsigned)__double2int_rz(cand) << kKeyBitsT) | (unsigned long long)kv;
+                    }
+                }
+            }
+            unsigned rb = team_ballot(relax, tbase);
+            if (team_ballot(overflow, tbase)) { status = NSFS_E_HEAP; rb = 0; if (phase == PH_SEARCH) phase = PH_FINAL; }
+            // ---- pushes, in NB_LUT order (astar.cpp:120) -------------------------------------------------------------
+            while (__any_sync(FULL, rb != 0u)) {
+                bool pushing = rb != 0u;
+                const int src = pushing ? __ffs(rb) - 1 : 0;
+                rb &= rb - 1u;
+                const unsigned long long v = __shfl_sync(FULL, entry, src, 8);
+                if (pushing && (long long)n >= p.heap_cap) { status = NSFS_E_HEAP; pushing = false; rb = 0; phase = PH_FINAL; }
+                team_push(heap, n, v, pushing, prio, tl, tbase);
+                if (pushing) { pushes++; if (n > peak) peak = n; }
+            }
+            if (phase == PH_SEARCH && n == 0u) phase = PH_FINAL;        // open list exhausted: unreachable (astar.cpp:129-135)
+        }
+
+        // ---- one step of the back-track for every team that found its goal (astar.cpp:70-82) ---------------------------
+        {
+            const bool walking = phase == PH_WALK;
+            uint32_t nk = 0;
+            if (walking && tl == 0) {
+                int32_t* out = p.paths ? p.paths + (size_t)qi * p.path_cap * 2 : nullptr;
+                if (out && plen < p.path_cap) { out[2 * plen] = (int)(wk / uW); out[2 * plen + 1] = (int)(wk % uW); }
+                if (wk != ks) {
+                    const uint32_t d = __ldcg(cells + wk).y & 7u;
+                    nk = wk - (uint32_t)(nb_di((int)d) * W + nb_dj((int)d));
+                }
+            }
+            nk = __shfl_sync(FULL, nk, 0, 8);
+            if (walking) {
+                plen++;
+                if (wk == ks || (long long)plen > p.N) phase = PH_FINAL;
+                else wk = nk;
+            }
+        }
+
+        // ---- results ------------------------------------------------------------------------------------------------
+        if (phase == PH_FINAL) {
+            if (tl == 0) {
+                if (status == NSFS_OK) {
+                    if (!found) {
+                        plen = 1;
+                        if (p.paths && p.path_cap > 0) {
+                            int32_t* out = p.paths + (size_t)qi * p.path_cap * 2;
+                            out[0] = (int)(ks / uW); out[1] = (int)(ks % uW);
+                        }
+                    }
+                    if (p.g_goal) {
+                        double gg = kInfD;
+                        if (kg != 0xffffffffu) {
+                            const uint2 c = __ldcg(cells + kg);
+                            if ((c.y >> 4) == epoch) gg = __dadd_rn((double)(c.x & 0xffffu), __dmul_rn((double)(c.x >> 16), kSqrt2D));
+                        }
+                        p.g_goal[qi] = gg;
+                    }
+                } else {
+                    plen = 1;
+                    if (p.g_goal) p.g_goal[qi] = kInfD;
+                }
+                if (p.status) p.status[qi] = status;
+                if (p.path_len) p.path_len[qi] = plen;
+                if (p.settled) p.settled[qi] = expansions;
+                if (p.stats5) {
+                    atomicAdd((unsigned long long*)p.stats5 + 0, (unsigned long long)pops);
+                    atomicAdd((unsigned long long*)p.stats5 + 1, (unsigned long long)expansions);
+                    atomicAdd((unsigned long long*)p.stats5 + 2, (unsigned long long)pushes);
+                    atomicMax((unsigned long long*)p.stats5 + 3, (unsigned long long)peak);
+                }
+            }
+            phase = PH_FETCH;
+        }
+        __syncwarp();
+    }
+    if (have_slot && tl == 0) p.epoch[slot] = epoch;
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+int team_alloc(nsfs_planner* h, int want_slots) {
+    TeamWork& s = h->team;
+    long long heap_cap = h->opt_team_heap_cap > 0 ? h->opt_team_heap_cap : (h->N / 8 > 4096 ? h->N / 8 : 4096);
+    if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;
+    if (want_slots < 1) want_slots = 1;
+    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * 24 * 4;    // 24 warps / SM x 4 teams
+    long long slots = want_slots < cap ? want_slots : cap;
+    if (s.cells && s.slots >= slots && s.heap_cap >= heap_cap) return NSFS_OK;
+    team_free(h);
+    size_t free_b = 0, total_b = 0;
+    NSFS_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+    const long long heap_stride = (heap_cap + 5) & ~1ll;
+    const size_t per_slot = (size_t)h->N * sizeof(uint2) + (size_t)heap_stride * sizeof(unsigned long long);
+    const long long fit = (long long)((double)free_b * 0.85 / (double)per_slot);
+    if (slots > fit) slots = fit;
+    if (slots < 1) return NSFS_E_NOMEM;
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.cells, (size_t)slots * (size_t)h->N * sizeof(uint2)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.heap, (size_t)slots * (size_t)heap_stride * sizeof(unsigned long long)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.epoch, (size_t)slots * sizeof(uint32_t)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.work_counter, sizeof(int)));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * (size_t)h->N * sizeof(uint2), h->stream));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.epoch, 0, (size_t)slots * sizeof(uint32_t), h->stream));
+    s.slots = (int)slots;
+    s.heap_cap = heap_cap;
+    return NSFS_OK;
+}
+
+void team_free(nsfs_planner* h) {
+    TeamWork& s = h->team;
+    cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter);
+    s = TeamWork();
+}
+
+int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status, double* d_g_goal,
+                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5) {
+    if (nq <= 0) return NSFS_OK;
+    int rc = team_alloc(h, nq);
+    if (rc != NSFS_OK) return rc;
+    TeamWork& s = h->team;
+    TeamParams p;
+    p.out_mask = h->d_out_mask; p.cells = s.cells; p.heap = s.heap; p.epoch = s.epoch; p.work_counter = s.work_counter;
+    p.H = h->H; p.W = h->W; p.N = h->N; p.heap_cap = s.heap_cap; p.heap_stride = (s.heap_cap + 5) & ~1ll;
+    p.slots = nq < s.slots ? nq : s.slots;
+    p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;
+    p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
+    p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
+    const int block = TEAM_WARPS_PER_BLOCK * 32;
+    const int per_block = TEAM_WARPS_PER_BLOCK * 4;
+    const int grid = (p.slots + per_block - 1) / per_block;
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+    if (algo == NSFS_ASTAR) search_team_kernel<NSFS_ASTAR><<<grid, block, 0, h->stream>>>(p);
+    else if (algo == NSFS_DJIKSTRA) search_team_kernel<NSFS_DJIKSTRA><<<grid, block, 0, h->stream>>>(p);
+    else return NSFS_E_ARG;
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+}  // namespace nsfs
