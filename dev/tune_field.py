@@ -13,7 +13,10 @@ inners = [int(x) for x in os.environ.get('INNERS', '1,2,4,8').split(',')]
 deltas = [float(x) for x in os.environ.get('DELTAS', '16,32,64,128,1000000').split(',')]
 idles = [int(x) for x in os.environ.get('IDLES', '100').split(',')]
 alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
-for inner, delta, alpha, idle in itertools.product(inners, deltas, alphas, idles):
+dins = [int(x) for x in os.environ.get('DINS', '12').split(',')]
+waits = [int(x) for x in os.environ.get('WAITS', '200').split(',')]
+for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, alphas, idles, dins, waits):
+    P.set_option('field_delta_in', din); P.set_option('field_wait_ns', wait)
     P.set_option('field_idle_ns', idle)
     P.set_option('field_alpha', alpha)
     P.set_option('field_inner', inner); P.set_option('field_delta', int(delta))
@@ -25,4 +28,4 @@ for inner, delta, alpha, idle in itertools.product(inners, deltas, alphas, idles
     g = P.field(src)['g']
     if ref is None: ref = g
     same = np.array_equal(ref, g)
-    print(f"idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)
+    print(f"din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)

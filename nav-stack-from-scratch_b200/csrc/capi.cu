@@ -595,6 +595,8 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
+    if (!strcmp(key, "field_delta_in")) { h->opt_field_delta_in = value; return NSFS_OK; }
+    if (!strcmp(key, "field_wait_ns")) { h->opt_field_wait_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_alpha")) { h->opt_field_alpha = value; return NSFS_OK; }
     if (!strcmp(key, "active_row_lo")) { h->opt_active_row_lo = value; h->have_map = false; return NSFS_OK; }   // masks depend on it: set the map again
     if (!strcmp(key, "active_row_hi")) { h->opt_active_row_hi = value; h->have_map = false; return NSFS_OK; }

@@ -46,6 +46,9 @@ constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending up
 #ifndef NSFS_FIELD_PROF
 #define NSFS_FIELD_PROF 0
 #endif
+#ifndef NSFS_FIELD_ORDERED
+#define NSFS_FIELD_ORDERED 1      // 0 = the first (flag-based, unordered) in-tile scheduler, kept for A/B measurements
+#endif
 
 struct FieldParams {
     unsigned long long* prof;   // [8] cycle/iteration counters when NSFS_FIELD_PROF
@@ -62,6 +65,8 @@ struct FieldParams {
     int inner;            // warp-local relaxations of an active sub-block per block-wide sweep
     float delta;          // width of the cost band [.., thr] the wavefront may advance into per round (delta-stepping)
     float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
+    float delta_in;       // ordered relaxation: a sub-block runs while its key is within delta_in of the tile's smallest due key
+    unsigned wait_ns;     // ... and otherwise waits this long before looking again
     uint32_t cap;         // float bits: tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it
                           // (kNoKey - 1 = no cap).  Used by the multi-GPU solve to advance all shards band by band.
 };
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) field_inject_kernel(FieldParams p, long l
 // stands, then raises s_ctl[1].  (Measured on B200, C2 input: 4.7 ms against 5.3 ms for barrier-per-sweep.)
 template <bool ASYNC_TILES>
 __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float thr, float* s, uint8_t* s_flag_, int* s_ctl_,
-                                           uint32_t* s_emin) {
+                                           uint32_t* s_emin, uint32_t* s_due, uint32_t key0) {
     volatile uint8_t* s_flag = s_flag_;
     volatile int* s_ctl = s_ctl_;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,7 +176,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         const long long key = (long long)(r0 - 1 + rr) * W + (c0 - 1 + cc);
         s[rr * SROW + (SCOL0 - 1) + cc] = (key >= 0 && key < N) ? __ldcg(p.g + key) : kInfF;   // L2: other SMs write g
     }
-    if (tid < NSB) s_flag[tid] = 1;                                   // first pass: everything is due
+    if (tid < NSB) { s_flag[tid] = 1; s_due[tid] = key0; }            // first pass: everything is due (ordered: at the tile's own key)
     if (tid < 12) s_emin[tid] = kNoKey;                               // slot 11: this tile's own pending key
     if (tid < 2) s_ctl[tid] = 0;
 
@@ -199,6 +204,107 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     long long t_b = clock64();
 #endif
 
+#if NSFS_FIELD_ORDERED
+    // ---- asynchronous relaxation in near-Dijkstra order -------------------------------------------------------
+    // Each sub-block carries a due KEY (the smallest value that changed next to it) instead of a flag.  A warp takes its
+    // due sub-block with the smallest key, but only while that key lies within delta_in of the smallest key due anywhere in
+    // the tile: the wavefront is relaxed in order, so a sub-block is rarely relaxed against values that are about to drop.
+    // (The warp holding the tile-wide minimum always qualifies, so there is always progress.)
+    {
+    volatile uint32_t* due = s_due;
+    bool counted_idle = false;
+    unsigned nap = p.wait_ns;                                         // idle back-off: short right after work, doubling up to idle_ns
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        const uint32_t k0 = due[warp * 4 + 0], k1 = due[warp * 4 + 1], k2 = due[warp * 4 + 2], k3 = due[warp * 4 + 3];
+        const uint32_t mymin = min(min(k0, k1), min(k2, k3));
+        bool did = false;
+        if (mymin != kNoKey) {
+            uint32_t gmin = mymin;
+            if (p.delta_in < 1e8f) {                                  // optional tile-wide gate (off by default: measured no gain)
+                uint32_t g4 = kNoKey;
+#pragma unroll
+                for (int t = 0; t < NSB / 32; ++t) g4 = min(g4, due[lane + 32 * t]);
+                gmin = min(mymin, __reduce_min_sync(0xffffffffu, g4));
+            }
+            if (__uint_as_float(mymin) <= __uint_as_float(gmin) + p.delta_in) {
+                const int q = mymin == k0 ? 0 : mymin == k1 ? 1 : mymin == k2 ? 2 : 3;
+                const int sb = warp + q * FIELD_WARPS;
+                if (counted_idle) {                                   // leave the idle count BEFORE consuming the key
+                    if (lane == 0) atomicSub(s_ctl_, 1);
+                    counted_idle = false;
+                }
+                __syncwarp();
+                if (lane == 0) atomicExch(s_due + warp * 4 + q, kNoKey);   // clear first, then read the neighbours
+                __syncwarp();
+                const volatile float* c = s + soff[q];
+                // registers cannot be indexed by a run-time q: select
+                const uint32_t m = q == 0 ? mask[0] : q == 1 ? mask[1] : q == 2 ? mask[2] : mask[3];
+                float vq = q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3];
+                const int so = q == 0 ? soff[0] : q == 1 ? soff[1] : q == 2 ? soff[2] : soff[3];
+                const volatile float* cc = s + so;
+                (void)c;
+                uint32_t bits = 0, last = 0;
+                float kchg = __uint_as_float(kNoKey);
+                for (int it = 0; it < p.inner; ++it) {
+                    float best = vq;
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) {
+                        const float nb = cc[-nb_di(d) * SROW - nb_dj(d)];
+                        const float cand = nb + (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f);
+                        if (((m >> d) & 1u) && cand <= thr) best = fminf(best, cand);
+                    }
+                    const bool changed = best < vq;
+                    if (changed) { vq = best; s[so] = best; ever |= 1u << q; kchg = fminf(kchg, best); }
+#if NSFS_FIELD_PROF
+                    my_iters++;
+#endif
+                    last = __ballot_sync(0xffffffffu, changed);
+                    if (!last) break;
+                    bits |= last;
+                    __syncwarp();
+                }
+                if (q == 0) v[0] = vq; else if (q == 1) v[1] = vq; else if (q == 2) v[2] = vq; else v[3] = vq;
+                if (bits) {
+                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, __float_as_uint(kchg));
+                    __syncwarp();
+                    if (lane < 9) {
+                        const int dy = lane / 3 - 1, dx = lane % 3 - 1;
+                        uint32_t need = (dy == 0 && dx == 0) ? last : bits;
+                        if (dy < 0) need &= 0x000000ffu; else if (dy > 0) need &= 0xff000000u;
+                        if (dx < 0) need &= 0x01010101u; else if (dx > 0) need &= 0x80808080u;
+                        const int sy = sb / SB_X + dy, sx = sb % SB_X + dx;
+                        const int t = sy * SB_X + sx;
+                        if (need && sy >= 0 && sy < SB_Y && sx >= 0 && sx < SB_X)
+                            atomicMin(s_due + (t % FIELD_WARPS) * SB_PER_WARP + t / FIELD_WARPS, kmin);
+                    }
+                }
+                did = true;
+                nap = p.wait_ns;
+            } else {
+                __nanosleep(p.wait_ns);                               // due, but ahead of the wavefront: not idle, just early
+                continue;
+            }
+        }
+        if (did) continue;
+        if (!counted_idle) {
+            int old = 0;
+            if (lane == 0) old = atomicAdd(s_ctl_, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            counted_idle = true;
+            if (old == FIELD_WARPS - 1) {                             // every warp is idle-counted: verify and finish
+                uint32_t g4 = kNoKey;
+#pragma unroll
+                for (int t = 0; t < NSB / 32; ++t) g4 = min(g4, due[lane + 32 * t]);
+                const bool any = __any_sync(0xffffffffu, g4 != kNoKey);
+                if (!any && s_ctl[0] == FIELD_WARPS && lane == 0) s_ctl[1] = 1;
+            }
+        }
+        if (s_ctl[1]) break;
+        __nanosleep(nap);
+        nap = min(nap * 2u, p.idle_ns);
+    }
+    }
+#else
     // ---- asynchronous relaxation -----------------------------------------------------------------------
     bool counted_idle = false;
     for (int spin = 0; spin < (1 << 26); ++spin) {
@@ -267,6 +373,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         if (s_ctl[1]) break;
         __nanosleep(p.idle_ns);
     }
+#endif
     __syncthreads();
 #if NSFS_FIELD_PROF
     long long t_c = clock64();
@@ -391,6 +498,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
     cg::grid_group grid = cg::this_grid();
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
+    __shared__ __align__(16) uint32_t s_due[NSB];
     __shared__ int s_ctl[2];
     __shared__ uint32_t s_emin[12];
     __shared__ int s_int[2];
@@ -413,7 +521,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
 #if NSFS_FIELD_PROF
         long long t_r0 = clock64();
 #endif
-        for (int t = blockIdx.x; t < n_cur; t += gridDim.x) relax_tile<false>(p, p.list[t], thr, s, s_flag, s_ctl, s_emin);
+        for (int t = blockIdx.x; t < n_cur; t += gridDim.x) relax_tile<false>(p, p.list[t], thr, s, s_flag, s_ctl, s_emin, s_due, __float_as_uint(fmaxf(thr - p.delta, 0.f)));
 #if NSFS_FIELD_PROF
         { long long dt = clock64() - t_r0; t_relax += dt;
           if (threadIdx.x == 0 && round < 4000) atomicMax(p.prof + 16 + round, (unsigned long long)dt); }
@@ -435,6 +543,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
 __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solve_async_kernel(FieldParams p) {
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
+    __shared__ __align__(16) uint32_t s_due[NSB];
     __shared__ int s_ctl[2];
     __shared__ uint32_t s_emin[12];
     __shared__ unsigned long long s_best;
@@ -471,7 +580,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         __syncthreads();
         const float thr = fminf(__uint_as_float(s_key) + p.delta, __uint_as_float(p.cap));
         __syncthreads();
-        relax_tile<true>(p, tile, thr, s, s_flag, s_ctl, s_emin);
+        relax_tile<true>(p, tile, thr, s, s_flag, s_ctl, s_emin, s_due, s_key);
         if (tid == 0) { __threadfence(); atomicSub(p.counts + 1, 1); }
     }
 }
@@ -599,6 +708,8 @@ static FieldParams field_params(nsfs_planner* h) {
     p.idle_ns = h->opt_field_idle_ns > 0 ? (unsigned)h->opt_field_idle_ns : 1000u;
     p.delta = h->opt_field_delta > 0 ? (float)h->opt_field_delta : 128.0f;
     p.alpha = h->opt_field_alpha >= 0 ? (float)h->opt_field_alpha / 100.0f : 0.5f;
+    p.delta_in = h->opt_field_delta_in > 0 ? (float)h->opt_field_delta_in : 1e9f;
+    p.wait_ns = h->opt_field_wait_ns > 0 ? (unsigned)h->opt_field_wait_ns : 200u;
     p.cap = kNoKey - 1u;
     return p;
 }

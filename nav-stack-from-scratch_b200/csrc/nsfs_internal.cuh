@@ -104,6 +104,8 @@ struct nsfs_planner {
     long long opt_field_mode = 0;       // 0 = asynchronous tile scheduling, 1 = bulk-synchronous rounds
     long long opt_field_idle_ns = 0;    // 0 = default (100)
     long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
+    long long opt_field_wait_ns = 0;    // ... back-off of a warp whose due sub-block is ahead of that band (0 = default 200)
     // row-partitioned shards: rows outside [active_row_lo, active_row_hi) take no in-edges (they only exist
     // so the masks of the rows next to them see the right neighbourhood); counts cover [count_row_lo, count_row_hi)
     long long opt_active_row_lo = 0, opt_active_row_hi = 0;   // hi == 0: all rows
