@@ -37,6 +37,7 @@ struct FieldWork {
     uint8_t*  pred = nullptr;      // [N]
     uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
     int*      list[2] = {nullptr, nullptr};
+    int*      tile_busy = nullptr; // [nTiles] dynamic scheduling: tile is being relaxed
     int*      counts = nullptr;    // [8]: 0 list length, 1 pending (async), 2 rounds, 3 tile visits, 4 error flag, 5 reached, 6 min pending key, 7 thr
     int       tiles_x = 0, tiles_y = 0;
     int       src_i = -1, src_j = -1;
@@ -101,9 +102,10 @@ struct nsfs_planner {
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
     long long opt_field_inner = 0;      // 0 = default (4)
     long long opt_field_delta = 0;      // 0 = default (64)
-    long long opt_field_mode = 0;       // 0 = asynchronous tile scheduling, 1 = bulk-synchronous rounds
+    long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
     long long opt_field_idle_ns = 0;    // 0 = default (100)
     long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    long long opt_field_groups = 0;     // dynamic tile scheduling: tile groups (0 = default)
     long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
     long long opt_field_wait_ns = 0;    // ... back-off of a warp whose due sub-block is ahead of that band (0 = default 200)
     // row-partitioned shards: rows outside [active_row_lo, active_row_hi) take no in-edges (they only exist

@@ -109,6 +109,10 @@ class FieldShard:
     def min_pending(self):
         return self.solver.min_pending()
 
+    def failed(self):
+        """A reached cell whose expansion throws in the reference (NSFS_E_RANGE): the whole solve stops, like the exception."""
+        return getattr(self.solver, "status", 0) != 0
+
     def finish(self):
         return self.solver.finish()
 
@@ -138,7 +142,7 @@ def solve_in_process(shards, src, band=DEFAULT_BAND, max_rounds=1000000):
             s.absorb(_snapshot(from_up), _snapshot(from_down))
         pend = [s.min_pending() for s in shards]
         m = min(pend)
-        if not m < INF:
+        if not m < INF or any(s.failed() for s in shards):
             break
         rounds += 1
         cap = _cap(m, band)
@@ -181,10 +185,11 @@ def solve_distributed(shard: FieldShard, src, dist, device=None, band=DEFAULT_BA
             torch.cuda.current_stream(device).synchronize()
         shard.absorb(recv_up, recv_down)
         pend = shard.min_pending()
-        flag = torch.tensor([pend if pend < INF else 3.0e38], dtype=torch.float32, device=device if device is not None else "cpu")
+        mine = -1.0 if shard.failed() else (pend if pend < INF else 3.0e38)      # a failed shard stops everybody
+        flag = torch.tensor([mine], dtype=torch.float32, device=device if device is not None else "cpu")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         m = float(flag.item())
-        if m >= 3.0e38:
+        if m >= 3.0e38 or m < 0.0:
             break
         rounds += 1
         cap = _cap(m, band)
