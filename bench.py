@@ -304,7 +304,10 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
             r = P.field_device((src[0] - a, src[1]))
             return dict(reached=r["reached"], rounds=1, kernel_ms=r["stats"]["main_kernel_ms"], dev_ms=r["stats"]["gpu_ms"],
                         visits=r["stats"]["tile_visits"])
-        out = sf.solve_distributed(shard, src, dist, dev, band=args.band if args.band > 0 else None)
+        if args.exchange == "p2p":
+            out = sf.solve_p2p(shard, src, dist, dev)
+        else:
+            out = sf.solve_distributed(shard, src, dist, dev, band=args.band if args.band > 0 else None)
         return dict(reached=out["result"]["reached"], rounds=out["rounds"],
                     kernel_ms=sum(s["main_kernel_ms"] for s in shard.solver.stats),
                     dev_ms=sum(s["gpu_ms"] for s in shard.solver.stats) + out["result"]["stats"]["gpu_ms"],
@@ -375,7 +378,7 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "units_per_step": "1 field over all ranks",
-                   "partition": f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, NCCL send/recv + 1 all-reduce per round, band {args.band:g}" if world > 1 else "single handle",
+                   "partition": f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, " + ("peer-to-peer posts over NVLink inside the solve kernel (no rounds)" if args.exchange == "p2p" else f"NCCL send/recv + 1 all-reduce per round, band {args.band:g}") if world > 1 else "single handle",
                    "l2": "flushed between timed steps (256 MiB fill)",
                    "timing": "wall clock between cuda synchronize + barrier on both sides, max over ranks (the step spans several kernels, NCCL and host round control)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -612,6 +615,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=28416, help="queries per step per GPU (c4): two waves of the 14 208 query slots (24 warps x 4 teams x 148 SMs)")
     ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "rounds"],
+                    help="c5 at N > 1: p2p = shards post boundary rows into each other's memory over NVLink from inside the solve "
+                         "kernel (one launch per GPU); rounds = NCCL send/recv + all-reduce per band")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -138,6 +138,30 @@ int nsfs_field_min_pending(nsfs_t* h, float* min_pending);   /* e.g. after nsfs_
 int nsfs_field_finish(nsfs_t* h, nsfs_stats* st);
 int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred);   /* valid after nsfs_field_begin */
 
+/* ---- peer-to-peer shards over NVLink (one process per GPU) ----------------------------------------------------
+ * Instead of exchange rounds, each shard's solve kernel pushes every improvement of its first / last two owned rows
+ * straight into the neighbour shard's ghost rows (remote atomicMin on the neighbour's g), wakes the neighbour's tiles
+ * (remote atomicMin on its tile keys) and all kernels share ONE counter of pending tiles, so a single launch per GPU runs
+ * every shard to the global fixed point.  Buffers travel between processes as CUDA IPC handles.
+ *   nsfs_field_peer_export(h, &info)                     after nsfs_set_map*; send info to the neighbours and rank 0's to all
+ *   nsfs_field_peer_attach(h, side, &nb_info, row_off)   side 0 = shard above, 1 = below; my local row r = its local row r + row_off
+ *   nsfs_field_peer_counter(h, &owner_info | NULL)       whose counter is shared (NULL: mine)
+ *   nsfs_field_peer_rows(h, own_lo, own_hi)              my owned local rows
+ *   per solve: nsfs_field_begin; nsfs_field_pending_count on every shard; sum; nsfs_field_set_counter(total) on the owner;
+ *              barrier; nsfs_field_relax_p2p on every shard; barrier; nsfs_field_finish. */
+typedef struct nsfs_peer_info {
+    unsigned char g[64], key[64], counts[64];             /* cudaIpcMemHandle_t of the g, tile-key and counter arrays */
+    int rows, W, tiles_x, tiles_y;
+} nsfs_peer_info;
+int nsfs_field_peer_export(nsfs_t* h, nsfs_peer_info* out);
+int nsfs_field_peer_attach(nsfs_t* h, int side, const nsfs_peer_info* nb, int row_off);
+int nsfs_field_peer_counter(nsfs_t* h, const nsfs_peer_info* owner);
+int nsfs_field_peer_rows(nsfs_t* h, int own_lo, int own_hi);
+int nsfs_field_peer_detach(nsfs_t* h);
+int nsfs_field_pending_count(nsfs_t* h, int* n_pending);
+int nsfs_field_set_counter(nsfs_t* h, int total);
+int nsfs_field_relax_p2p(nsfs_t* h, nsfs_stats* st);
+
 /* ---- fallback ------------------------------------------------------------------------------------
  * replaces: Djikstra::find_better_point(Index, MapData&) (djikstra.cpp:165-273) on a planner prepared
  * with cost mode "g" (global_planner.cpp:127-128).  (fi, fj) = first popped free cell, or the input cell

@@ -107,6 +107,8 @@ void nsfs_destroy(nsfs_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < 5; ++k)
+        if (h->field.ipc_opened[k]) cudaIpcCloseMemHandle(h->field.ipc_opened[k]);
     field_free(h);
     search_free(h);
     team_free(h);
@@ -467,6 +469,107 @@ int nsfs_field_relax_until(nsfs_t* h, float cap, float* min_pending, nsfs_stats*
     rc = field_read_counts(h, st, launches0, ms, tm.main_kernel_ms());
     if (min_pending) *min_pending = h->field.min_pending;
     return rc;
+}
+
+// ---- peer-to-peer shards -------------------------------------------------------------------------------------
+int nsfs_field_peer_export(nsfs_t* h, nsfs_peer_info* out) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!out) return NSFS_E_ARG;
+    if ((rc = field_alloc(h)) != NSFS_OK) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "nsfs_peer_info carries 64-byte IPC handles");
+    cudaIpcMemHandle_t hg, hk, hc;
+    NSFS_CUDA_TRY(h, cudaIpcGetMemHandle(&hg, h->field.g));
+    NSFS_CUDA_TRY(h, cudaIpcGetMemHandle(&hk, h->field.tile_key));
+    NSFS_CUDA_TRY(h, cudaIpcGetMemHandle(&hc, h->field.counts));
+    memcpy(out->g, &hg, 64); memcpy(out->key, &hk, 64); memcpy(out->counts, &hc, 64);
+    out->rows = h->H; out->W = h->W; out->tiles_x = h->field.tiles_x; out->tiles_y = h->field.tiles_y;
+    return NSFS_OK;
+}
+
+static int ipc_open(nsfs_planner* h, const unsigned char* raw, void** out, int slot) {
+    cudaIpcMemHandle_t hh;
+    memcpy(&hh, raw, 64);
+    if (h->field.ipc_opened[slot]) { cudaIpcCloseMemHandle(h->field.ipc_opened[slot]); h->field.ipc_opened[slot] = nullptr; }
+    NSFS_CUDA_TRY(h, cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess));
+    h->field.ipc_opened[slot] = *out;
+    return NSFS_OK;
+}
+
+int nsfs_field_peer_attach(nsfs_t* h, int side, const nsfs_peer_info* nb, int row_off) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (side < 0 || side > 1 || !nb || nb->W != h->W || nb->tiles_x != (h->W + 63) / 64) return NSFS_E_ARG;
+    if ((rc = field_alloc(h)) != NSFS_OK) return rc;
+    void *pg = nullptr, *pk = nullptr;
+    if ((rc = ipc_open(h, nb->g, &pg, 2 * side)) != NSFS_OK) return rc;
+    if ((rc = ipc_open(h, nb->key, &pk, 2 * side + 1)) != NSFS_OK) return rc;
+    h->field.peer_g[side] = (float*)pg; h->field.peer_key[side] = (uint32_t*)pk;
+    h->field.peer_row_off[side] = row_off; h->field.peer_tiles_y[side] = nb->tiles_y;
+    return NSFS_OK;
+}
+
+int nsfs_field_peer_counter(nsfs_t* h, const nsfs_peer_info* owner) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if ((rc = field_alloc(h)) != NSFS_OK) return rc;
+    if (!owner) {
+        if (h->field.ipc_opened[4]) { cudaIpcCloseMemHandle(h->field.ipc_opened[4]); h->field.ipc_opened[4] = nullptr; }
+        h->field.peer_counts = nullptr;
+        return NSFS_OK;
+    }
+    void* pc = nullptr;
+    if ((rc = ipc_open(h, owner->counts, &pc, 4)) != NSFS_OK) return rc;
+    h->field.peer_counts = (int*)pc;
+    return NSFS_OK;
+}
+
+int nsfs_field_peer_rows(nsfs_t* h, int own_lo, int own_hi) {
+    if (!h || own_lo < 0 || own_hi > h->H || own_hi - own_lo < 2) return NSFS_E_ARG;
+    h->field.own_lo = own_lo; h->field.own_hi = own_hi;
+    return NSFS_OK;
+}
+
+int nsfs_field_peer_detach(nsfs_t* h) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 5; ++k)
+        if (h->field.ipc_opened[k]) { cudaIpcCloseMemHandle(h->field.ipc_opened[k]); h->field.ipc_opened[k] = nullptr; }
+    for (int sd = 0; sd < 2; ++sd) { h->field.peer_g[sd] = nullptr; h->field.peer_key[sd] = nullptr; }
+    h->field.peer_counts = nullptr;
+    return NSFS_OK;
+}
+
+int nsfs_field_pending_count(nsfs_t* h, int* n_pending) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun || !n_pending) return NSFS_E_NOFIELD;
+    if ((rc = launch_field_count_pending(h)) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(n_pending, h->field.counts + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+int nsfs_field_set_counter(nsfs_t* h, int total) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->field.counts + 1, &total, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+int nsfs_field_relax_p2p(nsfs_t* h, nsfs_stats* st) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->field.begun) return NSFS_E_NOFIELD;
+    const long long launches0 = h->launches;
+    Timer tm(h);
+    if ((rc = launch_field_relax_p2p(h)) != NSFS_OK) return rc;
+    const float ms = tm.stop_sync();
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return field_read_counts(h, st, launches0, ms, tm.main_kernel_ms());
 }
 
 int nsfs_field_min_pending(nsfs_t* h, float* min_pending) {

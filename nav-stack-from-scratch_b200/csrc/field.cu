@@ -67,6 +67,14 @@ struct FieldParams {
     float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
     float delta_in;       // ordered relaxation: a sub-block runs while its key is within delta_in of the tile's smallest due key
     unsigned wait_ns;     // ... and otherwise waits this long before looking again
+    // peer-to-peer shards (NVLink): side 0 = the shard above (smaller rows), 1 = below.  A shard pushes every improvement
+    // of its first / last two OWNED rows straight into the neighbour's ghost rows and wakes the neighbour's tiles.
+    int* gcount;          // pending tiles + visits in flight: counts + 1, or ONE counter shared by all shards (on the owner's GPU)
+    float* peer_g[2];     // the neighbour's g array (its local rows), nullptr = no neighbour on that side
+    uint32_t* peer_key[2];
+    int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
+    int peer_tiles_y[2];
+    int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
     int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
     int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
     int dynamic;          // 1: any block takes the pending tile with the smallest key; 0: tile t belongs to block t % gridDim.x
@@ -180,7 +188,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         s[rr * SROW + (SCOL0 - 1) + cc] = (key >= 0 && key < N) ? __ldcg(p.g + key) : kInfF;   // L2: other SMs write g
     }
     if (tid < NSB) { s_flag[tid] = 1; s_due[tid] = key0; }            // first pass: everything is due (ordered: at the tile's own key)
-    if (tid < 12) s_emin[tid] = kNoKey;                               // slot 11: this tile's own pending key
+    if (tid < 16) s_emin[tid] = kNoKey;                               // slot 11: this tile's own pending key; 12 / 13: peer shards
     if (tid < 2) s_ctl[tid] = 0;
 
     // ---- this thread's four cells ---------------------------------------------------------------------
@@ -402,12 +410,33 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
 #pragma unroll
     for (int q = 0; q < SB_PER_WARP; ++q) {
         const bool ch = (ever >> q) & 1u;
-        if (ch) __stcg(p.g + key[q], v[q]);
-        if (!__any_sync(0xffffffffu, ch)) continue;
         const int sb = warp + q * FIELD_WARPS;
         const int sy = sb / SB_X, sx = sb % SB_X;
         const int ly = sy * SBH + lr, lx = sx * SBW + lc;
         const uint32_t vb = ch ? __float_as_uint(v[q]) : kNoKey;
+        if (ch) {
+            const int r = r0 + ly;
+            if (ASYNC_TILES && (p.peer_g[0] || p.peer_g[1])) {
+                if (r < p.own_lo || r >= p.own_hi) {
+                    // a ghost row: the neighbour shard lowers it too (remote atomicMin), so my store must not raise it
+                    atomicMin(reinterpret_cast<uint32_t*>(p.g) + key[q], vb);
+                } else {
+                    __stcg(p.g + key[q], v[q]);
+                    // my first / last two owned rows ARE the neighbour's ghost rows: push the value over NVLink
+                    if (p.peer_g[0] && r < p.own_lo + 2) {
+                        atomicMin(reinterpret_cast<uint32_t*>(p.peer_g[0]) + (long long)(r + p.peer_row_off[0]) * W + (c0 + lx), vb);
+                        atomicMin(s_emin + 12, vb);
+                    }
+                    if (p.peer_g[1] && r >= p.own_hi - 2) {
+                        atomicMin(reinterpret_cast<uint32_t*>(p.peer_g[1]) + (long long)(r + p.peer_row_off[1]) * W + (c0 + lx), vb);
+                        atomicMin(s_emin + 13, vb);
+                    }
+                }
+            } else {
+                __stcg(p.g + key[q], v[q]);
+            }
+        }
+        if (!__any_sync(0xffffffffu, ch)) continue;
         // slot (dy+1)*3 + (dx+1): neighbour tile (dy, dx) reads a cell of ours that changed; 9 / 10: map edge wrap
         auto post = [&](bool cond, int slot) {
             const uint32_t m = __reduce_min_sync(0xffffffffu, cond ? vb : kNoKey);
@@ -420,8 +449,28 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         if (tx == p.tiles_x - 1) post(c0 + lx == W - 1, 9);          // flat-key wrap: (r, W-1) feeds (r..r+2, 0)
         if (tx == 0 && sx == 0) post(lx == 0, 10);                    // flat-key wrap: (r, 0) feeds (r-2..r, W-1)
     }
-    __threadfence();       // the improved cells are visible before the keys that announce them
+    if (ASYNC_TILES && (p.peer_g[0] || p.peer_g[1])) __threadfence_system();   // ... also on the neighbour GPU
+    else __threadfence();  // the improved cells are visible before the keys that announce them
     __syncthreads();
+    if (ASYNC_TILES && tid >= 16 && tid < 32) {
+        // wake the neighbour shard's tiles that hold, or read as halo, the two rows just pushed: its rows R-3 .. R+4 lie in at
+        // most two tile rows; columns tx-1 .. tx+1 plus the far edge column when this tile touches a map edge (flat-key wrap)
+        const int side = (tid - 16) >> 3, slot = (tid - 16) & 7;
+        const uint32_t m = s_emin[12 + side];
+        if (p.peer_key[side] && m != kNoKey) {
+            const int R = (side == 0 ? p.own_lo : p.own_hi - 2) + p.peer_row_off[side];      // first pushed row, neighbour-local
+            const int tr0 = max(R - 3, 0) / TS, tr1 = min(R + 4, p.peer_tiles_y[side] * TS - 1) / TS;
+            const int trow = (slot & 1) ? tr1 : tr0;
+            const int cs = slot >> 1;                                      // 0..2: tx-1..tx+1, 3: the wrap column
+            int tcol = cs < 3 ? tx + cs - 1 : (tx == 0 ? p.tiles_x - 1 : (tx == p.tiles_x - 1 ? 0 : -1));
+            bool dup = ((slot & 1) && tr1 == tr0) || tcol < 0 || tcol >= p.tiles_x;
+            if (cs == 3 && !dup) dup = abs(tcol - tx) <= 1;                // already covered by the three neighbour columns
+            if (!dup) {
+                const uint32_t old = atomicMin(p.peer_key[side] + trow * p.tiles_x + tcol, m);
+                if (old > p.cap && m <= p.cap) atomicAdd(p.gcount, 1);
+            }
+        }
+    }
     {
         // key posts: <9 neighbour tiles, 9..11 right map edge -> left-edge tiles of tile rows ty-1..ty+1,
         // 12..14 left map edge -> right-edge tiles of rows ty-1..ty+1, 15 this tile's own rejected candidates
@@ -445,7 +494,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         }
         if (target >= 0 && m != kNoKey) {
             const uint32_t old = atomicMin(p.tile_key + target, m);
-            if (ASYNC_TILES && old > p.cap && m <= p.cap) atomicAdd(p.counts + 1, 1);     // a tile became pending (within the cap)
+            if (ASYNC_TILES && old > p.cap && m <= p.cap) atomicAdd(p.gcount, 1);     // a tile became pending (within the cap)
         }
     }
     if (tid == 0) atomicAdd(p.counts + 3, 1);
@@ -503,7 +552,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
     __shared__ __align__(16) uint8_t s_flag[NSB];
     __shared__ __align__(16) uint32_t s_due[NSB];
     __shared__ int s_ctl[2];
-    __shared__ uint32_t s_emin[12];
+    __shared__ uint32_t s_emin[16];
     __shared__ int s_int[2];
 
 #if NSFS_FIELD_PROF
@@ -548,7 +597,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
     __shared__ __align__(16) uint8_t s_flag[NSB];
     __shared__ __align__(16) uint32_t s_due[NSB];
     __shared__ int s_ctl[2];
-    __shared__ uint32_t s_emin[12];
+    __shared__ uint32_t s_emin[16];
     __shared__ unsigned long long s_best;
     __shared__ uint32_t s_key;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -578,7 +627,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         const unsigned long long pick = s_best;
         if (pick == ~0ull) {
             int pending = 1;
-            if (tid == 0) { pending = atomicAdd(p.counts + 1, 0); s_key = (uint32_t)pending; }
+            if (tid == 0) { pending = atomicAdd(p.gcount, 0); s_key = (uint32_t)pending; }
             __syncthreads();
             pending = (int)s_key;
             __syncthreads();
@@ -612,7 +661,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         if (tid == 0) {
             __threadfence();
             if (p.dynamic) atomicExch(p.tile_busy + tile, 0);
-            atomicSub(p.counts + 1, 1);
+            if (p.peer_g[0] || p.peer_g[1]) __threadfence_system();
+            atomicSub(p.gcount, 1);
         }
     }
 }
@@ -735,6 +785,9 @@ static FieldParams field_params(nsfs_planner* h) {
     FieldParams p;
     p.g = f.g; p.in_mask = h->d_in_mask; p.tile_key = f.tile_key; p.list = f.list[0];
     p.tile_busy = f.tile_busy;
+    p.gcount = f.counts + 1;
+    for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; }
+    p.own_lo = 0; p.own_hi = h->H;
     // dynamic tile claiming (field_mode 2) is an option, not the default: on C2 one global queue cuts tile visits by 30 % but
     // herds the blocks onto the same few tiles (4.6 ms against 2.5 ms); 37 groups measured 2.33 ms, within noise of static
     p.dynamic = h->opt_field_mode == 2 ? 1 : 0;
@@ -819,6 +872,42 @@ int launch_field_relax(nsfs_planner* h, float cap) {
       fprintf(stderr, "[field prof] grid %d: per-block avg cycles: kernel %.0f relax %.0f | tile sums: load %.0f sweeps %.0f tail %.0f (cycles, summed over visits) | sub-block iterations %llu\n",
               grid, (double)hp[4] / grid, (double)hp[5] / grid, (double)hp[0], (double)hp[1], (double)hp[2], hp[3]); }
 #endif
+    return NSFS_OK;
+}
+
+// Peer-to-peer solve: the shared pending counter was set by the host (sum of every shard's pending tiles), every shard's
+// kernel runs until the GLOBAL count is zero.  No cap, no rounds.
+int launch_field_relax_p2p(nsfs_planner* h) {
+    FieldWork& f = h->field;
+    FieldParams p = field_params(h);
+    for (int sd = 0; sd < 2; ++sd) {
+        p.peer_g[sd] = f.peer_g[sd]; p.peer_key[sd] = f.peer_key[sd];
+        p.peer_row_off[sd] = f.peer_row_off[sd]; p.peer_tiles_y[sd] = f.peer_tiles_y[sd];
+    }
+    if (f.own_hi > f.own_lo) { p.own_lo = f.own_lo; p.own_hi = f.own_hi; }
+    p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
+    p.dynamic = 0;
+    int per_sm = 0;
+    NSFS_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_solve_async_kernel, FIELD_THREADS, 0));
+    if (per_sm < 1) return set_cuda_error(h, cudaErrorLaunchOutOfResources, "field_solve_async_kernel occupancy");
+    int grid = per_sm * h->sm_count;
+    const int n_tiles = f.tiles_x * f.tiles_y;
+    if (grid > n_tiles) grid = n_tiles;
+    void* args[] = {&p};
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+    NSFS_CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)field_solve_async_kernel, dim3(grid), dim3(FIELD_THREADS), args, 0, h->stream));
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, n_tiles, p.cap, f.counts, 1);
+    h->launches += 2;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
+int launch_field_count_pending(nsfs_planner* h) {
+    FieldWork& f = h->field;
+    field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, kNoKey - 1u, f.counts, 0);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;
 }
 

@@ -42,6 +42,14 @@ struct FieldWork {
     int       tiles_x = 0, tiles_y = 0;
     int       src_i = -1, src_j = -1;
     bool      valid = false;       // solved and finished: nsfs_field_path may walk pred
+    // peer-to-peer shards: neighbours' buffers opened through CUDA IPC (other processes) and the shared pending counter
+    float*    peer_g[2] = {nullptr, nullptr};
+    uint32_t* peer_key[2] = {nullptr, nullptr};
+    int       peer_row_off[2] = {0, 0};
+    int       peer_tiles_y[2] = {0, 0};
+    int*      peer_counts = nullptr;          // the counter owner's counts array (nullptr: mine)
+    void*     ipc_opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int       own_lo = 0, own_hi = 0;         // owned local rows (0, 0 = all)
     float     min_pending = 0.f;   // smallest tile key left pending by the last relax (+inf = none)
     bool      begun = false;       // g holds a field in progress (nsfs_field_begin or a full solve ran)
 };
@@ -128,6 +136,8 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
 int launch_field_begin(nsfs_planner* h, int si, int sj);
 int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved);
 int launch_field_relax(nsfs_planner* h, float cap);
+int launch_field_relax_p2p(nsfs_planner* h);
+int launch_field_count_pending(nsfs_planner* h);
 int launch_field_finish(nsfs_planner* h);
 int launch_field_min_pending(nsfs_planner* h);
 int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap, int* d_n, double* d_cost, int* d_status);

@@ -36,6 +36,12 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PeerInfo(C.Structure):
+    """nsfs_peer_info: CUDA IPC handles of a shard's g / tile-key / counter arrays (picklable through bytes())."""
+    _fields_ = [("g", C.c_ubyte * 64), ("key", C.c_ubyte * 64), ("counts", C.c_ubyte * 64),
+                ("rows", C.c_int), ("W", C.c_int), ("tiles_x", C.c_int), ("tiles_y", C.c_int)]
+
+
 _lib = None
 
 
@@ -68,6 +74,14 @@ def lib():
         L.nsfs_field_min_pending.argtypes = [vp, C.POINTER(C.c_float)]
         L.nsfs_field_finish.argtypes = [vp, C.POINTER(Stats)]
         L.nsfs_field_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.nsfs_field_peer_export.argtypes = [vp, C.POINTER(PeerInfo)]
+        L.nsfs_field_peer_attach.argtypes = [vp, i32, C.POINTER(PeerInfo), i32]
+        L.nsfs_field_peer_counter.argtypes = [vp, C.POINTER(PeerInfo)]
+        L.nsfs_field_peer_rows.argtypes = [vp, i32, i32]
+        L.nsfs_field_peer_detach.argtypes = [vp]
+        L.nsfs_field_pending_count.argtypes = [vp, C.POINTER(i32)]
+        L.nsfs_field_set_counter.argtypes = [vp, i32]
+        L.nsfs_field_relax_p2p.argtypes = [vp, C.POINTER(Stats)]
         L.nsfs_field_path.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(dbl)]
         L.nsfs_find_better_point.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(Stats)]
         L.nsfs_find_better_point_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(Stats)]
@@ -231,6 +245,43 @@ class Planner:
         dg, dp = C.c_void_p(), C.c_void_p()
         self._check(self.L.nsfs_field_pointers(self.h, C.byref(dg), C.byref(dp)))
         return dg.value, dp.value
+
+    # -- peer-to-peer shards (NVLink, one process per GPU) -------------------------------------------
+    def field_peer_export(self):
+        info = PeerInfo()
+        self._check(self.L.nsfs_field_peer_export(self.h, C.byref(info)))
+        return bytes(info)
+
+    def field_peer_attach(self, side, info_bytes, row_off):
+        info = PeerInfo.from_buffer_copy(info_bytes)
+        self._check(self.L.nsfs_field_peer_attach(self.h, int(side), C.byref(info), int(row_off)))
+
+    def field_peer_counter(self, info_bytes=None):
+        if info_bytes is None:
+            self._check(self.L.nsfs_field_peer_counter(self.h, None))
+        else:
+            info = PeerInfo.from_buffer_copy(info_bytes)
+            self._check(self.L.nsfs_field_peer_counter(self.h, C.byref(info)))
+
+    def field_peer_rows(self, own_lo, own_hi):
+        self._check(self.L.nsfs_field_peer_rows(self.h, int(own_lo), int(own_hi)))
+
+    def field_peer_detach(self):
+        self._check(self.L.nsfs_field_peer_detach(self.h))
+
+    def field_pending_count(self):
+        n = C.c_int(0)
+        self._check(self.L.nsfs_field_pending_count(self.h, C.byref(n)))
+        return n.value
+
+    def field_set_counter(self, total):
+        self._check(self.L.nsfs_field_set_counter(self.h, int(total)))
+
+    def field_relax_p2p(self):
+        st = Stats()
+        rc = self.L.nsfs_field_relax_p2p(self.h, C.byref(st))
+        self._check(rc, allow=(E_RANGE,))
+        return dict(status=rc, min_pending=self.field_min_pending(), stats=st.asdict())
 
     def field_path(self, goal, cap=None):
         cap = int(cap if cap is not None else self.N + 1)

@@ -198,6 +198,39 @@ def solve_distributed(shard: FieldShard, src, dist, device=None, band=DEFAULT_BA
     return dict(rounds=rounds, result=shard.finish())
 
 
+def solve_p2p(shard: FieldShard, src, dist, device):
+    """One shard per process / GPU, NO exchange rounds: every shard's solve kernel pushes its boundary rows into the
+    neighbour's memory over NVLink and wakes the neighbour's tiles itself (remote atomics); one shared counter of pending
+    tiles ends all kernels together.  Host-side work per solve: seed, one all-reduce to prime the counter, two barriers."""
+    import torch
+
+    rank, world = shard.rank, shard.part.world
+    P = shard.solver.P
+    if not getattr(shard, "_p2p_ready", False):
+        infos = [None] * world
+        dist.all_gather_object(infos, P.field_peer_export())
+        lo = [shard.part.held(r)[0] for r in range(world)]
+        if rank > 0:
+            P.field_peer_attach(0, infos[rank - 1], lo[rank] - lo[rank - 1])
+        if rank < world - 1:
+            P.field_peer_attach(1, infos[rank + 1], lo[rank] - lo[rank + 1])
+        P.field_peer_counter(None if rank == 0 else infos[0])
+        P.field_peer_rows(shard.loc(shard.r0), shard.loc(shard.r1))
+        shard._p2p_ready = True
+    shard.start(src)
+    n = torch.tensor([P.field_pending_count()], dtype=torch.int64, device=device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        P.field_set_counter(int(n.item()))
+    dist.barrier()                       # the counter is primed before any kernel may decrement it
+    r = P.field_relax_p2p()
+    shard.solver.stats.append(r["stats"])
+    shard.solver.status = shard.solver.status or r["status"]
+    shard.relaxes += 1
+    dist.barrier()                       # every shard is at the global fixed point
+    return dict(rounds=1, result=shard.finish())
+
+
 # ---- the GPU solver: one nsfs handle over the shard's held rows ----------------------------------------------------
 class GpuShardSolver:
     """nsfs.capi.Planner over rows [lo, hi) of the global map; row values travel as torch CUDA tensors."""

@@ -93,3 +93,21 @@ def test_shard_without_source_and_unreachable_rows(gpu_lib):
     assert out["results"][3]["reached"] == 0
     for s in shards:
         s.solver.close()
+
+
+def test_peer_to_peer_shards_over_nvlink():
+    """N >= 2 GPUs: one solve kernel per GPU, boundary rows and tile keys posted into the neighbour's memory with remote
+    atomics, one shared pending counter (nsfs_field_relax_p2p).  Bit-identical to the single-handle field."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on one node")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", "p2p_worker.py")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-3000:]
