@@ -78,6 +78,10 @@ void nsfs_destroy(nsfs_t* h);
  * inflated planes and the per-cell edge masks on the device. */
 int nsfs_set_map(nsfs_t* h, const int32_t* infl, const int32_t* lo, int lo_thresh);          /* host pointers   */
 int nsfs_set_map_device(nsfs_t* h, const int32_t* d_infl, const int32_t* d_lo, int lo_thresh); /* device pointers */
+/* Only rows [row0, row0 + nrows) changed since the last nsfs_set_map (host pointers to nrows x W cells of each plane):
+ * uploads those rows and rebuilds only the bit-plane words and edge masks that can see them (rows +-4).  Same result as
+ * nsfs_set_map with the whole updated planes.  Needs a map set by nsfs_set_map (NSFS_E_NOMAP otherwise). */
+int nsfs_update_map_rows(nsfs_t* h, int row0, int nrows, const int32_t* infl_rows, const int32_t* lo_rows);
 /* Packed planes for shipping a map between GPUs (N/4 bytes instead of 8N): words = (H*W + 31) / 32 each. */
 int nsfs_map_words(const nsfs_t* h);
 int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_t** d_inflated);

@@ -138,12 +138,34 @@ int nsfs_set_map(nsfs_t* h, const int32_t* infl, const int32_t* lo, int lo_thres
     h->lo_thresh = lo_thresh;
     rc = launch_pack_map(h, h->d_infl, h->d_lo);
     if (rc != NSFS_OK) return rc;
-    return finish_map(h);
+    rc = finish_map(h);
+    h->have_raw = rc == NSFS_OK;
+    return rc;
+}
+
+// Rows [row0, row0 + nrows) of the caller's planes changed since the last nsfs_set_map: upload only those rows and
+// rebuild only what can see them (the reference re-reads the whole MapData on every call; its maps arrive at 25 Hz and
+// a lidar sweep touches a few rows' worth of cells, global_planner.cpp:65-73, occupancy_grid.cpp:166-196).
+int nsfs_update_map_rows(nsfs_t* h, int row0, int nrows, const int32_t* infl_rows, const int32_t* lo_rows) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->have_raw) return NSFS_E_NOMAP;                 // needs the int32 planes of nsfs_set_map on the device
+    if (row0 < 0 || nrows < 0 || row0 + nrows > h->H || (nrows && (!infl_rows || !lo_rows))) return NSFS_E_ARG;
+    if (!nrows) return NSFS_OK;
+    const size_t off = (size_t)row0 * h->W, bytes = (size_t)nrows * h->W * sizeof(int32_t);
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_infl + off, infl_rows, bytes, cudaMemcpyHostToDevice, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lo + off, lo_rows, bytes, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_update_rows(h, row0, nrows)) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->field.valid = false;
+    h->field.begun = false;
+    return NSFS_OK;
 }
 
 int nsfs_set_map_device(nsfs_t* h, const int32_t* d_infl, const int32_t* d_lo, int lo_thresh) {
     int rc = enter(h, false);
     if (rc != NSFS_OK) return rc;
+    h->have_raw = false;
     if (!d_infl || !d_lo || ((uintptr_t)d_infl & 15) || ((uintptr_t)d_lo & 15)) return NSFS_E_ARG;   // 128-bit loads
     h->lo_thresh = lo_thresh;
     rc = launch_pack_map(h, d_infl, d_lo);
@@ -164,6 +186,7 @@ int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_
 int nsfs_set_packed_map_device(nsfs_t* h, const uint32_t* d_free, const uint32_t* d_inflated) {
     int rc = enter(h, false);
     if (rc != NSFS_OK) return rc;
+    h->have_raw = false;
     if (!d_free || !d_inflated) return NSFS_E_ARG;
     const size_t bytes = (size_t)((h->N + 31) / 32) * 4;
     if (d_free != h->d_free) NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_free, d_free, bytes, cudaMemcpyDeviceToDevice, h->stream));

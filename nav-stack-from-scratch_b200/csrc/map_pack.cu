@@ -16,8 +16,8 @@ namespace nsfs {
 // OR their nibbles into one 32-bit word with three xor-shuffles.  HBM-bound: 8 B/cell in, 0.25 B/cell out.
 __global__ void __launch_bounds__(256) pack_map_kernel(const int32_t* __restrict__ infl, const int32_t* __restrict__ lo,
                                                        int lo_thresh, long long N, uint32_t* __restrict__ free_bits,
-                                                       uint32_t* __restrict__ infl_bits, long long n_words) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 cells
+                                                       uint32_t* __restrict__ infl_bits, long long n_words, long long word0) {
+    const long long t = word0 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 cells (word0: partial re-pack)
     const long long k0 = t * 4;
     uint32_t fn = 0, in_ = 0;
     if (k0 + 3 < N) {
@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(256) pack_map_kernel(const int32_t* __restrict
 
 // ---- kernel 2: out-edge masks ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N,
-                                                       uint16_t* __restrict__ out_mask) {
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= N) return;
+                                                       uint16_t* __restrict__ out_mask, long long k0, long long k1) {
+    const long long u = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= k1) return;
     const int i = (int)(u / W);
     uint32_t pass = 0, diag = 0, thr = 0, card = 1;
 #pragma unroll
@@ -76,9 +76,10 @@ __global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restric
 // ---- kernel 3: in-edge masks (pull form used by the field relaxation) --------------------------------
 __global__ void __launch_bounds__(256) in_mask_kernel(const uint32_t* __restrict__ free_bits,
                                                       const uint16_t* __restrict__ out_mask, int H, int W, long long N,
-                                                      long long active_lo, long long active_hi, uint16_t* __restrict__ in_mask) {
-    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
+                                                      long long active_lo, long long active_hi, uint16_t* __restrict__ in_mask,
+                                                      long long k0, long long k1) {
+    const long long v = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= k1) return;
     uint32_t m = 0;
     if (bit_at(free_bits, v) && v >= active_lo && v < active_hi) {    // rows outside the window take no in-edges (shards)
 #pragma unroll
@@ -109,27 +110,45 @@ __global__ void test_pos_kernel(const uint32_t* __restrict__ free_bits, int H, i
     out[t] = r;
 }
 
-int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo) {
+// Packs the words that hold cells [k0, k1) (whole map: 0, N).
+static int pack_range(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo, long long k0, long long k1) {
     const long long n_words = (h->N + 31) / 32;
-    const long long threads = n_words * 8;
+    const long long w0 = k0 / 32, w1 = (k1 + 31) / 32;
+    const long long threads = (w1 - w0) * 8;
+    if (threads <= 0) return NSFS_OK;
     const int block = 256;
     const long long grid = (threads + block - 1) / block;
-    pack_map_kernel<<<(unsigned)grid, block, 0, h->stream>>>(d_infl, d_lo, h->lo_thresh, h->N, h->d_free, h->d_inflated, n_words);
+    pack_map_kernel<<<(unsigned)grid, block, 0, h->stream>>>(d_infl, d_lo, h->lo_thresh, h->N, h->d_free, h->d_inflated, w1 < n_words ? w1 : n_words, w0);
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;
 }
 
-int launch_build_masks(nsfs_planner* h) {
+int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo) { return pack_range(h, d_infl, d_lo, 0, h->N); }
+
+// Edge masks of cells [k0, k1) (out) and [j0, j1) (in).
+static int mask_range(nsfs_planner* h, long long k0, long long k1, long long j0, long long j1) {
     const int block = 256;
-    const long long grid = (h->N + block - 1) / block;
-    out_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, h->d_out_mask);
     const long long a_lo = (h->opt_active_row_lo > 0 ? h->opt_active_row_lo : 0) * (long long)h->W;
     const long long a_hi = h->opt_active_row_hi > 0 ? h->opt_active_row_hi * (long long)h->W : h->N;
-    in_mask_kernel<<<(unsigned)grid, block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, a_lo, a_hi, h->d_in_mask);
+    if (k1 > k0) out_mask_kernel<<<(unsigned)((k1 - k0 + block - 1) / block), block, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, h->d_out_mask, k0, k1);
+    if (j1 > j0) in_mask_kernel<<<(unsigned)((j1 - j0 + block - 1) / block), block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, a_lo, a_hi, h->d_in_mask, j0, j1);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;
+}
+
+int launch_build_masks(nsfs_planner* h) { return mask_range(h, 0, h->N, 0, h->N); }
+
+// Rows [row0, row0 + nrows) of the int32 planes changed (already in d_infl / d_lo): re-pack their words and rebuild the
+// masks that can see them.  A cell's out-edges depend on free bits up to 2 rows away (flat-key wrap at the column edges),
+// a cell's in-edges on out-masks up to 2 rows away: out-masks of rows +-2, in-masks of rows +-4.
+int launch_update_rows(nsfs_planner* h, int row0, int nrows) {
+    const long long W = h->W;
+    int rc = pack_range(h, h->d_infl, h->d_lo, row0 * W, (row0 + nrows) * W);
+    if (rc != NSFS_OK) return rc;
+    auto clampk = [&](long long r) { return (r < 0 ? 0 : (r > h->H ? h->H : r)) * W; };
+    return mask_range(h, clampk(row0 - 2), clampk(row0 + nrows + 2), clampk(row0 - 4), clampk(row0 + nrows + 4));
 }
 
 int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out) {

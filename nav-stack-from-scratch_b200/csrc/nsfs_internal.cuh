@@ -128,6 +128,7 @@ namespace nsfs {
 // Every launcher returns NSFS_OK or NSFS_E_CUDA and bumps h->launches by the kernels it launched.
 int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo);
 int launch_build_masks(nsfs_planner* h);
+int launch_update_rows(nsfs_planner* h, int row0, int nrows);
 int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out);
 
 int field_alloc(nsfs_planner* h);

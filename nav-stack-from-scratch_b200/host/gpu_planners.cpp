@@ -258,6 +258,49 @@ std::shared_ptr<GpuDjikstra> make_fallback_planner(const PlannerConfig& cfg, Map
     return p;
 }
 
+// ---- one plan request ---------------------------------------------------------------------------------------------
+bool test_pos(Pos2D pos, MapData& map_data) {
+    // GlobalPlanner::testPos (global_planner.cpp:384-408) with its own pos2idx / flatten / oob (360-376): the key is formed
+    // before the row-only bounds test, and vector::at throws for a key outside the grids
+    const int i = (int)std::round((pos.x - map_data.origin_.x) / map_data.cell_size_);
+    const int j = (int)std::round((pos.y - map_data.origin_.y) / map_data.cell_size_);
+    const int key = i * map_data.map_size_.j + j;
+    if (i < 0 || i >= map_data.map_size_.i) return false;
+    if (map_data.grid_inflation_.at((size_t)key) > 0) return false;
+    if (map_data.grid_logodds_.at((size_t)key) > map_data.lo_thresh_) return false;
+    return true;
+}
+
+PlanRequestResult serve_plan_request(GridPlannerCore& main_planner, GpuDjikstra& fallback_planner, Pos2D robot_position, Pos2D current_goal,
+                                     MapData& map_data) {
+    PlanRequestResult r;
+    r.robot_ok = test_pos(robot_position, map_data);
+    r.goal_ok = test_pos(current_goal, map_data);
+    r.goal = current_goal;
+    r.backup_robot = robot_position;
+    Pos2D start = robot_position;
+    if (r.robot_ok && r.goal_ok) {
+        r.which_case = 1;                                                       // global_planner.cpp:179-185
+    } else if (r.robot_ok && !r.goal_ok) {
+        r.which_case = 2;                                                       // 188-214
+        r.goal = fallback_planner.find_better_point(current_goal, map_data);
+        r.goal_updated = true;
+    } else if (!r.robot_ok && r.goal_ok) {
+        r.which_case = 3;                                                       // 217-236
+        r.backup_robot = fallback_planner.find_better_point(robot_position, map_data);
+        r.backup_mode = true;
+        start = r.backup_robot;
+    } else {
+        r.which_case = 4;                                                       // 238-273: robot first, then the goal
+        r.backup_robot = fallback_planner.find_better_point(robot_position, map_data);
+        r.goal = fallback_planner.find_better_point(current_goal, map_data);
+        r.goal_updated = true;
+        start = r.backup_robot;                                                 // (upstream leaves backup_mode_ as it was here)
+    }
+    r.path = main_planner.generatePath(start, r.goal, map_data);
+    return r;
+}
+
 }  // namespace nsfs_host
 
 // ---- C shim: lets the Python tests drive the C++ children exactly as GlobalPlanner::run would -----------------
@@ -353,6 +396,20 @@ int nsfsh_find_better_point_idx(void* p, int bi, int bj, double* fx, double* fy)
         const bot_utils::Pos2D r = s->fallback->find_better_point(bot_utils::Index(bi, bj), s->map);
         *fx = r.x; *fy = r.y;
         return 0;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+// serve_plan_request through the session's planners.  info[0..3] = case, goal_updated, backup_mode, robot_ok | goal_ok << 1
+int nsfsh_plan_request(void* p, double rx, double ry, double gx, double gy, double* out_xy, int cap, int* n, int* info, double* goal_xy,
+                       double* backup_xy) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        const nsfs_host::PlanRequestResult r = nsfs_host::serve_plan_request(*s->main_planner, *s->fallback, bot_utils::Pos2D(rx, ry),
+                                                                             bot_utils::Pos2D(gx, gy), s->map);
+        info[0] = r.which_case; info[1] = r.goal_updated; info[2] = r.backup_mode; info[3] = (int)r.robot_ok | ((int)r.goal_ok << 1);
+        goal_xy[0] = r.goal.x; goal_xy[1] = r.goal.y; backup_xy[0] = r.backup_robot.x; backup_xy[1] = r.backup_robot.y;
+        return emit(r.path, out_xy, cap, n);
     } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
     catch (const std::exception& e) { s->error = e.what(); return 2; }
 }

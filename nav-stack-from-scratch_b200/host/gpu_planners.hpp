@@ -122,4 +122,20 @@ std::shared_ptr<GridPlannerCore> make_main_planner(const PlannerConfig& cfg, bot
 // The fallback planner: a Djikstra prepared with cost mode "g" (global_planner.cpp:127-128).
 std::shared_ptr<GpuDjikstra> make_fallback_planner(const PlannerConfig& cfg, bot_utils::MapData& map_data);
 
+// ---- one plan request, as GlobalPlanner::run serves it (global_planner.cpp:164-273) ---------------------------------
+// Test the robot and goal cells (GlobalPlanner::testPos, global_planner.cpp:384-408, on the caller's MapData); repair
+// whichever is not free with the fallback planner (cases 2-4: 188-273); then generatePath.  No ROS in here: the caller
+// publishes `path` (writeToPathMsg) and, when goal_updated, tells the mission planner (192-205).
+struct PlanRequestResult {
+    std::vector<bot_utils::Pos2D> path;     // goal -> start, post-processed
+    int which_case = 0;                     // 1: both ok, 2: goal repaired, 3: robot repaired (backup_mode_), 4: both repaired
+    bool robot_ok = false, goal_ok = false;
+    bool goal_updated = false;              // current_goal_ was replaced by `goal`
+    bool backup_mode = false;               // the path starts at `backup_robot`, not at the robot
+    bot_utils::Pos2D goal, backup_robot;
+};
+bool test_pos(bot_utils::Pos2D pos, bot_utils::MapData& map_data);
+PlanRequestResult serve_plan_request(GridPlannerCore& main_planner, GpuDjikstra& fallback_planner, bot_utils::Pos2D robot_position,
+                                     bot_utils::Pos2D current_goal, bot_utils::MapData& map_data);
+
 }  // namespace nsfs_host

@@ -58,6 +58,7 @@ def lib():
         L.nsfs_destroy.restype = None
         L.nsfs_set_map.argtypes = [vp, vp, vp, i32]
         L.nsfs_set_map_device.argtypes = [vp, vp, vp, i32]
+        L.nsfs_update_map_rows.argtypes = [vp, i32, i32, vp, vp]
         L.nsfs_map_words.argtypes = [vp]
         L.nsfs_get_packed_map_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.nsfs_set_packed_map_device.argtypes = [vp, vp, vp]
@@ -144,6 +145,13 @@ class Planner:
         lo = np.ascontiguousarray(lo, np.int32)
         assert infl.size == self.N and lo.size == self.N
         self._check(self.L.nsfs_set_map(self.h, _ptr(infl), _ptr(lo), int(lo_thresh)))
+
+    def update_map_rows(self, row0, infl_rows, lo_rows):
+        """Rows [row0, row0 + len(infl_rows)) changed since set_map: upload and rebuild only what can see them."""
+        infl_rows = np.ascontiguousarray(infl_rows, np.int32).reshape(-1, self.W)
+        lo_rows = np.ascontiguousarray(lo_rows, np.int32).reshape(-1, self.W)
+        assert infl_rows.shape == lo_rows.shape
+        self._check(self.L.nsfs_update_map_rows(self.h, int(row0), len(infl_rows), _ptr(infl_rows), _ptr(lo_rows)))
 
     def set_map_device(self, d_infl_ptr, d_lo_ptr, lo_thresh=10):
         self._check(self.L.nsfs_set_map_device(self.h, C.c_void_p(d_infl_ptr), C.c_void_p(d_lo_ptr), int(lo_thresh)))

@@ -19,7 +19,7 @@ HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
 
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
-           "nsfsh_main_planner_kind", "nsfsh_sparsify")
+           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request")
 
 _libs = {}
 
@@ -45,6 +45,7 @@ def lib(so_path=None):
         L.nsfsh_load_config.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]
         L.nsfsh_main_planner_kind.argtypes = [vp]
         L.nsfsh_sparsify.argtypes = [vp, i32, vp, i32]
+        L.nsfsh_plan_request.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32, C.POINTER(i32), vp, vp, vp]
         _libs[path] = L
     return _libs[path]
 
@@ -127,6 +128,26 @@ class Session:
 
     def generate_path_pos(self, start_xy, goal_xy):
         return self._path(self.L.nsfsh_generate_path_pos, float(start_xy[0]), float(start_xy[1]), float(goal_xy[0]), float(goal_xy[1]))
+
+    def plan_request(self, robot_xy, goal_xy):
+        """GlobalPlanner::run's plan request (global_planner.cpp:164-273): test both cells, repair with the fallback, plan."""
+        cap = 4 * (self.H + self.W) + 64
+        while True:
+            out = np.zeros((cap, 2), np.float64)
+            n, info = C.c_int(0), np.zeros(4, np.int32)
+            goal, backup = np.zeros(2, np.float64), np.zeros(2, np.float64)
+            rc = self.L.nsfsh_plan_request(self.s, float(robot_xy[0]), float(robot_xy[1]), float(goal_xy[0]), float(goal_xy[1]),
+                                           out.ctypes.data_as(C.c_void_p), cap, C.byref(n), info.ctypes.data_as(C.c_void_p),
+                                           goal.ctypes.data_as(C.c_void_p), backup.ctypes.data_as(C.c_void_p))
+            if rc == 1:
+                return dict(status="out_of_range")
+            if rc != 0:
+                raise PlannerError(self.L.nsfsh_error(self.s).decode())
+            if n.value <= cap:
+                return dict(status="ok", path=out[: n.value].copy(), case=int(info[0]), goal_updated=bool(info[1]),
+                            backup_mode=bool(info[2]), robot_ok=bool(info[3] & 1), goal_ok=bool(info[3] & 2),
+                            goal=tuple(goal), backup_robot=tuple(backup))
+            cap = n.value
 
     def find_better_point(self, bad, as_pos=False):
         fx, fy = C.c_double(0), C.c_double(0)

@@ -67,6 +67,41 @@ def test_c4_batch_1024_subset_against_oracle(gpu_lib, oracle_mod):
     P.close()
 
 
+def test_c4_every_query_of_a_768_slice_against_the_cpu_planner(gpu_lib, oracle_mod):
+    """SURVEY.md 8d C4 asks for parity on a fixed subset of the 65,536 queries when the host is small: here EVERY query of a
+    768-query slice is replayed by the CPU planner (the reference's own Astar when oracle/_ref is present, else the
+    restatement), one planner instance per host thread, and compared: status, settled cells, path length, g(goal), and
+    the full path for every 8th query."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    infl, lo = mapgen.synth_map(1024, 1024, 0.10, 7)
+    nq = 768
+    qs = mapgen.sample_queries(infl, lo, 4096, 7)[1000:1000 + nq].copy()          # a slice from the middle of the workload
+    P = gpu_lib.Planner(1024, 1024)
+    P.set_map(infl, lo)
+    b = P.plan_batch("astar", "f", qs, path_cap=4096)
+    P.close()
+    threads = max(1, min(os.cpu_count() or 1, 32))
+    if oracle_mod.have_reference():
+        r = oracle_mod.Reference(infl, lo).plan_batch(0, "f", qs, nthreads=threads)      # the reference's own Astar::plan
+        assert r["status"] == 0 and (b["status"] == 0).all()
+        assert np.array_equal(b["settled"], r["settled"]) and np.array_equal(b["path_len"], r["path_len"])
+        assert same_cost(b["g_goal"], r["g_goal"])
+    O = [oracle_mod.Oracle(infl, lo) for _ in range(threads)]
+
+    def run(t):
+        return [(qi, O[t].plan(0, "f", qs[qi][:2], qs[qi][2:])) for qi in range(t, nq, threads)]
+
+    with ThreadPoolExecutor(threads) as ex:                                           # ctypes releases the GIL inside nso_plan
+        for chunk in ex.map(run, range(threads)):
+            for qi, o in chunk:
+                assert b["status"][qi] == o["status"] and b["settled"][qi] == o["settled"], qi
+                assert b["path_len"][qi] == len(o["path"]) and same_cost(b["g_goal"][qi], o["g_goal"]), qi
+                if qi % 8 == 0:
+                    assert np.array_equal(b["paths"][qi][:len(o["path"])], o["path"]), qi
+
+
 def test_c3_thetastar_4096_paths_are_line_of_sight_chains(gpu_lib):
     """BASELINE config 2 (C3): ThetaStar on the 4096x4096 cluttered map.  No reference exists (thetastar.cpp is
     empty), so the checks are structural: consecutive path vertices see each other, the chain is no longer than

@@ -149,3 +149,54 @@ def test_map_replaced_between_calls_like_the_ros_callbacks(host_mod, golden, ora
     b = S.generate_path_idx(q[:2], q[2:])["path"]
     assert np.array_equal(b, oracle_mod.Oracle(infl, lo_b).generate_path(0, "f", q[:2], q[2:])["final_xy"])
     S.close()
+
+
+@pytest.mark.gpu
+def test_plan_request_four_cases_like_global_planner_run(host_mod, oracle_mod):
+    """global_planner.cpp:164-273: both ok -> plan; bad goal / bad robot / both -> fallback repair(s), then plan.  The pieces
+    are checked against the CPU planner: find_better_point's cell, then generatePath from the repaired ends."""
+    from nsfs import mapgen
+    infl, lo = mapgen.synth_map(96, 120, 0.004, 81, inflated=True)
+    O = oracle_mod.Oracle(infl, lo)
+    free = mapgen.sample_free_cells(infl, lo, 4, 81)
+    bad = mapgen.sample_blocked_interior(infl, lo, 4, 81, margin=6)
+    S = host_mod.Session("astar", "f", infl, lo)
+    pos = lambda c: (c[0] * 0.05, c[1] * 0.05)
+    for case, robot, goal in ((1, free[0], free[1]), (2, free[2], bad[0]), (3, bad[1], free[3]), (4, bad[2], bad[3])):
+        r = S.plan_request(pos(robot), pos(goal))
+        assert r["status"] == "ok" and r["case"] == case
+        assert r["robot_ok"] == (case in (1, 2)) and r["goal_ok"] == (case in (1, 3))
+        start = robot if case in (1, 2) else O.find_better_point(robot)["cell"]
+        end = goal if case in (1, 3) else O.find_better_point(goal)["cell"]
+        assert r["goal_updated"] == (case in (2, 4)) and r["backup_mode"] == (case == 3)
+        assert r["goal"] == pos(end) and (case in (1, 2) or r["backup_robot"] == pos(start))
+        assert np.array_equal(r["path"], O.generate_path(0, "f", start, end)["final_xy"])
+    S.close()
+
+
+@pytest.mark.gpu
+def test_dirty_rows_update_equals_a_full_upload(gpu_lib):
+    """nsfs_update_map_rows: only the changed rows travel and only the masks that can see them are rebuilt; every
+    downstream result must equal a planner that received the whole updated map."""
+    from nsfs import mapgen
+    infl, lo = mapgen.synth_map(300, 260, 0.10, 82)
+    infl2, lo2 = infl.copy(), lo.copy()
+    rng = np.random.RandomState(82)
+    for (a, b) in ((0, 3), (130, 141), (296, 300)):                       # top edge, middle, bottom edge
+        blk = rng.rand(b - a, 260) < 0.2
+        infl2[a:b] = np.where(blk, 1, 0); lo2[a:b] = np.where(blk, 20, 0)
+        infl2[a:b, 0] = infl2[a:b, -1] = 1; lo2[a:b, 0] = lo2[a:b, -1] = 20
+    infl2[0] = infl2[-1] = 1; lo2[0] = lo2[-1] = 20
+    A = gpu_lib.Planner(300, 260); A.set_map(infl, lo)
+    for (a, b) in ((0, 3), (130, 141), (296, 300)):
+        A.update_map_rows(a, infl2[a:b], lo2[a:b])
+    B = gpu_lib.Planner(300, 260); B.set_map(infl2, lo2)
+    every = np.stack(np.meshgrid(np.arange(300), np.arange(260), indexing="ij"), -1).reshape(-1, 2)
+    assert np.array_equal(A.test_pos(every), B.test_pos(every))
+    src = mapgen.sample_free_cells(infl2, lo2, 1, 82)[0]
+    fa, fb = A.field(src), B.field(src)
+    assert np.array_equal(fa["g"], fb["g"]) and np.array_equal(fa["pred"], fb["pred"])
+    qs = mapgen.sample_queries(infl2, lo2, 24, 82)
+    pa, pb = A.plan_batch("astar", "f", qs, path_cap=1024), B.plan_batch("astar", "f", qs, path_cap=1024)
+    assert np.array_equal(pa["paths"], pb["paths"]) and np.array_equal(pa["settled"], pb["settled"])
+    A.close(); B.close()
