@@ -82,6 +82,13 @@ int nsfs_set_map_device(nsfs_t* h, const int32_t* d_infl, const int32_t* d_lo, i
  * uploads those rows and rebuilds only the bit-plane words and edge masks that can see them (rows +-4).  Same result as
  * nsfs_set_map with the whole updated planes.  Needs a map set by nsfs_set_map (NSFS_E_NOMAP otherwise). */
 int nsfs_update_map_rows(nsfs_t* h, int row0, int nrows, const int32_t* infl_rows, const int32_t* lo_rows);
+/* The map producer's last step on the device (reference loco_mapping, occupancy_grid.cpp:73-89,166-213): the caller hands over
+ * only the log-odds plane; the inflation plane (number of cells with log-odds >= occ_thresh whose disc mask covers the cell, with
+ * the reference's flat-key / row-0 quirks) is computed on the GPU, then the map is packed as by nsfs_set_map.  Halves the upload.
+ * inflation_radius / cell_size as in generateMask (0.2 / 0.05 upstream).  NSFS_E_RANGE: the reference's updateInflation would
+ * have thrown (an occupied cell's disc runs past the last cell).  nsfs_get_inflation copies the plane back (tests). */
+int nsfs_set_map_logodds(nsfs_t* h, const int32_t* lo, int lo_thresh, int occ_thresh, double inflation_radius, double cell_size);
+int nsfs_get_inflation(nsfs_t* h, int32_t* infl_out);
 /* Packed planes for shipping a map between GPUs (N/4 bytes instead of 8N): words = (H*W + 31) / 32 each. */
 int nsfs_map_words(const nsfs_t* h);
 int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_t** d_inflated);

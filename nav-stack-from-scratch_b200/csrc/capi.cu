@@ -143,6 +143,39 @@ int nsfs_set_map(nsfs_t* h, const int32_t* infl, const int32_t* lo, int lo_thres
     return rc;
 }
 
+int nsfs_set_map_logodds(nsfs_t* h, const int32_t* lo, int lo_thresh, int occ_thresh, double inflation_radius, double cell_size) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!lo || !(cell_size > 0.0) || !(inflation_radius >= 0.0)) return NSFS_E_ARG;
+    const size_t bytes = (size_t)h->N * sizeof(int32_t);
+    if (!h->d_infl) {
+        NSFS_CUDA_TRY(h, cudaMalloc(&h->d_infl, bytes + 16));
+        NSFS_CUDA_TRY(h, cudaMalloc(&h->d_lo, bytes + 16));
+    }
+    const size_t occ_bytes = ((size_t)((h->N + 31) / 32) + 8) * 4;
+    if ((rc = ensure_scratch(h, 256 + occ_bytes)) != NSFS_OK) return rc;
+    h->have_map = false; h->have_raw = false;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lo, lo, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = launch_inflate(h, h->d_lo, occ_thresh, inflation_radius, cell_size, h->d_infl, (uint32_t*)((char*)h->d_scratch + 256), (int*)h->d_scratch);
+    if (rc != NSFS_OK) return rc;
+    int flags = 0;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&flags, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->lo_thresh = lo_thresh;
+    if ((rc = launch_pack_map(h, h->d_infl, h->d_lo)) != NSFS_OK) return rc;
+    if ((rc = finish_map(h)) != NSFS_OK) return rc;
+    h->have_raw = true;
+    return (flags & 1) ? NSFS_E_RANGE : NSFS_OK;
+}
+
+int nsfs_get_inflation(nsfs_t* h, int32_t* infl_out) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!h->have_raw || !infl_out) return NSFS_E_ARG;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(infl_out, h->d_infl, (size_t)h->N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
 // Rows [row0, row0 + nrows) of the caller's planes changed since the last nsfs_set_map: upload only those rows and
 // rebuild only what can see them (the reference re-reads the whole MapData on every call; its maps arrive at 25 Hz and
 // a lidar sweep touches a few rows' worth of cells, global_planner.cpp:65-73, occupancy_grid.cpp:166-196).

@@ -58,6 +58,8 @@ def lib():
         L.nsfs_destroy.restype = None
         L.nsfs_set_map.argtypes = [vp, vp, vp, i32]
         L.nsfs_set_map_device.argtypes = [vp, vp, vp, i32]
+        L.nsfs_set_map_logodds.argtypes = [vp, vp, i32, i32, dbl, dbl]
+        L.nsfs_get_inflation.argtypes = [vp, vp]
         L.nsfs_update_map_rows.argtypes = [vp, i32, i32, vp, vp]
         L.nsfs_map_words.argtypes = [vp]
         L.nsfs_get_packed_map_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -145,6 +147,19 @@ class Planner:
         lo = np.ascontiguousarray(lo, np.int32)
         assert infl.size == self.N and lo.size == self.N
         self._check(self.L.nsfs_set_map(self.h, _ptr(infl), _ptr(lo), int(lo_thresh)))
+
+    def set_map_logodds(self, lo, lo_thresh=10, occ_thresh=10, inflation_radius=0.2, cell_size=0.05):
+        """Only the log-odds plane travels; the inflation plane is computed on the device (the map producer's last step)."""
+        lo = np.ascontiguousarray(lo, np.int32)
+        assert lo.size == self.N
+        rc = self.L.nsfs_set_map_logodds(self.h, _ptr(lo), int(lo_thresh), int(occ_thresh), float(inflation_radius), float(cell_size))
+        self._check(rc, allow=(E_RANGE,))
+        return rc
+
+    def inflation(self):
+        out = np.zeros((self.H, self.W), np.int32)
+        self._check(self.L.nsfs_get_inflation(self.h, _ptr(out)))
+        return out
 
     def update_map_rows(self, row0, infl_rows, lo_rows):
         """Rows [row0, row0 + len(infl_rows)) changed since set_map: upload and rebuild only what can see them."""

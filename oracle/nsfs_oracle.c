@@ -552,3 +552,44 @@ double nso_field_min_pending(const nso_map* m, const double* g, int row_lo, int 
         }
     return best;
 }
+
+/* ---- map producer, one step before the planner path -------------------------------------------
+ * generateMask (occupancy_grid.cpp:73-89): the (i, j) offsets with i*i + j*j <= r^2 / cell^2, i and j looped as doubles from
+ * -round(r / cell) to +round(r / cell).  Returns the number of offsets written to ab (pairs). */
+int nso_occ_mask(double inflation_radius, double cell_size, int32_t* ab, int cap) {
+    const double cells_in_radius = round(inflation_radius / cell_size);
+    const double furthest_away = inflation_radius * inflation_radius / cell_size / cell_size;
+    int n = 0;
+    for (double i = -cells_in_radius; i <= cells_in_radius; ++i)
+        for (double j = -cells_in_radius; j <= cells_in_radius; ++j)
+            if (i * i + j * j <= furthest_away) {
+                if (n < cap) { ab[2 * n] = (int32_t)i; ab[2 * n + 1] = (int32_t)j; }
+                n++;
+            }
+    return n;
+}
+
+/* The inflation plane the reference holds for a given log-odds plane.  It keeps it incrementally (updateLogOdds /
+ * updateInflation, occupancy_grid.cpp:166-213: +1 over the mask when a cell reaches thresh, -1 when it drops below), so at
+ * any time infl[k] = number of cells at or above thresh whose mask reaches k, under the reference's index rules:
+ * oob() tests only the row and with "<= 0" (220-223), so row 0 is never updated and never a target; the target key is
+ * (ci + a) * W + (cj + b) with an unchecked column (flatten, 215-218); a key outside [0, N) makes vector::at throw.
+ * Returns NSO_OK, or NSO_E_RANGE when some occupied cell's update would have thrown. */
+int nso_occ_inflation(int H, int W, const int32_t* lo, int thresh, const int32_t* ab, int n_mask, int32_t* infl) {
+    const long long N = (long long)H * W;
+    int status = NSO_OK;
+    for (long long k = 0; k < N; ++k) infl[k] = 0;
+    for (int ci = 1; ci < H; ++ci)                       /* updateLogOdds returns at once for row 0 (oob) */
+        for (int cj = 0; cj < W; ++cj) {
+            if (lo[(long long)ci * W + cj] < thresh) continue;
+            for (int m = 0; m < n_mask; ++m) {
+                const int ti = ci + ab[2 * m], tj = cj + ab[2 * m + 1];
+                if (ti <= 0 || ti >= H) continue;        /* oob(to_inflate): the column is never tested */
+                const long long key = (long long)ti * W + tj;
+                if (key < 0 || key >= N) { status = NSO_E_RANGE; continue; }
+                infl[key] += 1;
+            }
+        }
+    return status;
+}
+

@@ -60,6 +60,10 @@ int nso_field_fixed_point(const nso_map* m, int si, int sj, double* g);
 long long nso_field_relax_window(const nso_map* m, double* g, int row_lo, int row_hi, double slack, double cap);
 double nso_field_min_pending(const nso_map* m, const double* g, int row_lo, int row_hi, double slack);
 
+/* Map producer (reference loco_mapping): disc mask and the inflation plane implied by a log-odds plane. */
+int nso_occ_mask(double inflation_radius, double cell_size, int32_t* ab, int cap);
+int nso_occ_inflation(int H, int W, const int32_t* lo, int thresh, const int32_t* ab, int n_mask, int32_t* infl);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,84 @@ def have_reference() -> bool:
     return os.path.exists(REF_SO)
 
 
+REF_OCC_SO = os.path.join(HERE, "_ref", "libnsfs_ref_occ.so")
+
+
+def have_reference_occ() -> bool:
+    return os.path.exists(REF_OCC_SO)
+
+
+def occ_mask(inflation_radius=0.2, cell_size=0.05):
+    """generateMask restated (oracle/nsfs_oracle.c nso_occ_mask): int32 [n, 2] offsets."""
+    build()
+    lib = C.CDLL(ORACLE_SO)
+    lib.nso_occ_mask.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_int]
+    ab = np.zeros((4096, 2), np.int32)
+    n = lib.nso_occ_mask(float(inflation_radius), float(cell_size), ab.ctypes.data_as(C.c_void_p), 4096)
+    return ab[:n].copy()
+
+
+def occ_inflation(lo, thresh=10, inflation_radius=0.2, cell_size=0.05):
+    """(status, infl): the inflation plane the reference holds for this log-odds plane (nso_occ_inflation)."""
+    build()
+    lib = C.CDLL(ORACLE_SO)
+    lo = np.ascontiguousarray(lo, np.int32)
+    H, W = lo.shape
+    ab = occ_mask(inflation_radius, cell_size)
+    infl = np.zeros((H, W), np.int32)
+    lib.nso_occ_inflation.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = lib.nso_occ_inflation(H, W, lo.ctypes.data_as(C.c_void_p), int(thresh), ab.ctypes.data_as(C.c_void_p), len(ab),
+                               infl.ctypes.data_as(C.c_void_p))
+    return rc, infl
+
+
+class ReferenceOcc:
+    """The reference's OccupancyGrid node class, unmodified, behind oracle/ref_occ_harness.cpp (oracle/_ref only)."""
+
+    def __init__(self, min_xy=(0.0, 0.0), max_xy=(10.0, 10.0), cell=0.05, inflation_radius=0.2, thresh=10, cap=20, max_range=3.499999):
+        self.lib = C.CDLL(REF_OCC_SO)
+        L = self.lib
+        L.nsref_occ_create.restype = C.c_void_p
+        L.nsref_occ_create.argtypes = [C.c_double] * 6 + [C.c_int, C.c_int, C.c_double]
+        L.nsref_occ_destroy.argtypes = [C.c_void_p]
+        L.nsref_occ_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.nsref_occ_integrate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.nsref_occ_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.nsref_occ_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nsref_occ_mask.argtypes = [C.c_void_p, C.c_void_p]
+        self.ctx = L.nsref_occ_create(min_xy[0], min_xy[1], max_xy[0], max_xy[1], cell, inflation_radius, thresh, cap, max_range)
+        h, w, n = C.c_int(0), C.c_int(0), C.c_int(0)
+        L.nsref_occ_size(self.ctx, C.byref(h), C.byref(w), C.byref(n))
+        self.H, self.W, self.n_mask = h.value, w.value, n.value
+
+    def __del__(self):
+        try:
+            self.lib.nsref_occ_destroy(self.ctx)
+        except Exception:
+            pass
+
+    def integrate(self, poses, ranges):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 3)
+        ranges = np.ascontiguousarray(ranges, np.float32).reshape(len(poses), 360)
+        return self.lib.nsref_occ_integrate(self.ctx, len(poses), poses.ctypes.data_as(C.c_void_p), ranges.ctypes.data_as(C.c_void_p))
+
+    def update(self, ij, occupy):
+        ij = np.ascontiguousarray(ij, np.int32).reshape(-1, 2)
+        occupy = np.ascontiguousarray(occupy, np.uint8)
+        return self.lib.nsref_occ_update(self.ctx, len(ij), ij.ctypes.data_as(C.c_void_p), occupy.ctypes.data_as(C.c_void_p))
+
+    def planes(self):
+        lo = np.zeros((self.H, self.W), np.int32)
+        infl = np.zeros((self.H, self.W), np.int32)
+        self.lib.nsref_occ_get(self.ctx, lo.ctypes.data_as(C.c_void_p), infl.ctypes.data_as(C.c_void_p))
+        return lo, infl
+
+    def mask(self):
+        ab = np.zeros((self.n_mask, 2), np.int32)
+        self.lib.nsref_occ_mask(self.ctx, ab.ctypes.data_as(C.c_void_p))
+        return ab
+
+
 class _Stats(C.Structure):
     _fields_ = [("pops", C.c_longlong), ("expansions", C.c_longlong), ("pushes", C.c_longlong),
                 ("heap_peak", C.c_longlong), ("los_checks", C.c_longlong)]

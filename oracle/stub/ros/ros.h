@@ -35,4 +35,38 @@
 #define ROS_INFO_STREAM_COND(c, x) NSFS_STUB_COND(c, x)
 #define ROS_WARN_STREAM_COND(c, x) NSFS_STUB_COND(c, x)
 
+// ---- just enough of the node API for src/loco_mapping/src/occupancy_grid.cpp to compile and RUN its scan loop ----------
+// Parameters come from a global table (nsfs_stub::params), ros::spinOnce() calls a hook the harness installs (it plays the
+// role of the pose / scan callbacks), publishers swallow their messages.
+#include <functional>
+#include <map>
+#include <memory>
+namespace nsfs_stub {
+inline std::map<std::string, double>& params() { static std::map<std::string, double> p; return p; }
+inline std::function<void()>& spin_hook() { static std::function<void()> h; return h; }
+inline std::function<bool()>& keep_running() { static std::function<bool()> h; return h; }
+}
+namespace ros {
+struct Subscriber {};
+struct Publisher { template <class M> void publish(const M&) const {} };
+struct Rate { explicit Rate(double) {} void sleep() {} };
+inline bool ok() { return true; }
+inline void spinOnce() { if (nsfs_stub::spin_hook()) nsfs_stub::spin_hook()(); }
+class NodeHandle {
+public:
+    template <class T> bool param(const std::string& name, T& out, const T& def) const {
+        auto it = nsfs_stub::params().find(name);
+        if (it == nsfs_stub::params().end()) { out = def; return false; }
+        out = static_cast<T>(it->second);
+        return true;
+    }
+    bool param(const std::string& name, bool def) const {          // nh_.param("trigger_nodes", true): the loop condition
+        if (name == "trigger_nodes" && nsfs_stub::keep_running()) return nsfs_stub::keep_running()();
+        return def;
+    }
+    template <class M, class C> Subscriber subscribe(const std::string&, int, void (C::*)(M), C*) { return Subscriber(); }
+    template <class M> Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
+};
+}
+
 #endif
