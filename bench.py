@@ -507,7 +507,7 @@ def ours(args):
             return int(r["settled"].sum())
 
         h2d, d2h = nq * 16, nq * (4 + 8 + 4 + 8)
-        main_kernel = "search_kernel"
+        main_kernel = "search_team_kernel" if (args.workload == "c4" and nq == 28416) else ("search_team_kernel(batch)" if nq > 1 and algo != "thetastar" else "search_kernel")
 
     # ---- warm-up, then exactly K timed steps (device time of each step's kernels; L2 flushed between steps) ----
     sampler = ClockSampler(local) if rank == 0 else None
