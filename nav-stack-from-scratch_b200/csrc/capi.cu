@@ -291,12 +291,18 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     NSFS_CUDA_TRY(h, cudaMemsetAsync(d + o_s5, 0, 5 * 8, h->stream));
     if (path_elems) NSFS_CUDA_TRY(h, cudaMemsetAsync(d + o_paths, 0, path_elems * 4, h->stream));   // cells beyond path_len read as 0
     const bool team = use_team_kernel(h, kind, algo, nq);
-    if (!team && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
+    // find_better_point runs with its state in shared memory unless the wide kernel is forced (the re-run path below)
+    const bool small_fb = kind == 1 && h->opt_search_kernel != 1 && h->W >= 3;
+    if (!team && !small_fb && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
     if (team && (rc = team_alloc(h, nq)) != NSFS_OK) return rc;
     Timer tm(h);
-    rc = launch_any_search(h, team, kind, algo, mode, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (double*)(d + o_g),
-                           (int32_t*)(d + o_len), (long long*)(d + o_set), path_elems ? (int32_t*)(d + o_paths) : nullptr, path_cap,
-                           (long long*)(d + o_s5));
+    if (small_fb)
+        rc = launch_fallback_small(h, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (long long*)(d + o_set),
+                                   (int32_t*)(d + o_paths), (long long*)(d + o_s5));
+    else
+        rc = launch_any_search(h, team, kind, algo, mode, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (double*)(d + o_g),
+                               (int32_t*)(d + o_len), (long long*)(d + o_set), path_elems ? (int32_t*)(d + o_paths) : nullptr, path_cap,
+                               (long long*)(d + o_s5));
     if (rc != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
@@ -316,7 +322,7 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     long long worst = 8 * h->N + 16;
     if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;      // search_alloc clamps to 32-bit heap positions
     for (int q = 0; q < nq; ++q) {
-        if (stat_h[q] != NSFS_E_HEAP || (!team && h->search.heap_cap >= worst)) continue;
+        if (stat_h[q] != NSFS_E_HEAP || (!team && !small_fb && h->search.heap_cap >= worst)) continue;
         const long long keep_cap = h->opt_heap_cap, keep_slots = h->opt_max_slots, keep_kernel = h->opt_search_kernel;
         h->opt_heap_cap = worst; h->opt_max_slots = 1; h->opt_search_kernel = 1;
         search_free(h);

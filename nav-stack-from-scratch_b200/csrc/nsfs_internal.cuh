@@ -158,6 +158,9 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
 int launch_inflate(nsfs_planner* h, const int32_t* d_lo, int occ_thresh, double inflation_radius, double cell_size, int32_t* d_infl,
                    uint32_t* d_occ_scratch, int* d_flags);
 
+int launch_fallback_small(nsfs_planner* h, int nq, const int32_t* d_q, int32_t* d_status, long long* d_settled, int32_t* d_cells,
+                          long long* d_stats5);
+
 int launch_los_batch(nsfs_planner* h, int n, const int32_t* d_seg4, int8_t* d_out);
 int launch_any_angle(nsfs_planner* h, int n, const int32_t* d_pts, uint8_t* d_keep);
 

@@ -401,6 +401,145 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(
     if (lane == 0) p.epoch[slot] = epoch;
 }
 
+// ---- find_better_point with its whole state in shared memory -----------------------------------------------------
+// The fallback search touches a handful of cells around the bad cell (10-16 on average), so a dense per-cell
+// store (16 B x N per slot: 4 GB on the 16384^2 map) is the wrong shape for it.  Here each warp keeps the touched cells in
+// a 256-slot open-addressed table and the open list in 256 heap positions, both in shared memory; the replay itself (same
+// heap primitives, same fp64 sums, same NB_LUT push order) is unchanged.  A search that outgrows the table ends with
+// NSFS_E_HEAP and the C-ABI re-runs it on the wide kernel, so results never depend on which kernel ran.
+constexpr int FB_CAP = 256;
+constexpr int FB_MAX_CELLS = 128;
+constexpr uint32_t FB_EMPTY = 0xffffffffu;
+struct FbState {
+    unsigned long long heap[FB_CAP + 8];
+    double g[FB_CAP];
+    uint32_t key[FB_CAP];
+    uint8_t vis[FB_CAP];
+};
+
+__device__ __forceinline__ int fb_find(const FbState& st, uint32_t key) {           // slot of key, or -1
+    uint32_t s0 = (key * 2654435761u) >> 24;
+    for (int probe = 0; probe < FB_CAP; ++probe) {
+        const uint32_t k = st.key[s0];
+        if (k == key) return (int)s0;
+        if (k == FB_EMPTY) return -1;
+        s0 = (s0 + 1) & (FB_CAP - 1);
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int fb_insert(FbState& st, uint32_t key) {               // one thread; the key is known to be absent
+    uint32_t s0 = (key * 2654435761u) >> 24;
+    while (st.key[s0] != FB_EMPTY) s0 = (s0 + 1) & (FB_CAP - 1);
+    st.key[s0] = key;
+    st.vis[s0] = 0;
+    return (int)s0;
+}
+
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) fallback_small_kernel(SearchParams p) {
+    __shared__ __align__(16) FbState sm[SEARCH_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31;
+    FbState& st = sm[threadIdx.x >> 5];
+    const int W = p.W, H = p.H;
+    const uint32_t uW = (uint32_t)W;
+    const Prio prio = make_prio(NSFS_MODE_G);                   // the fallback planner is prepared with cost mode "g" (global_planner.cpp:127)
+    const LaneNode ln = lane_node(lane);
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(p.work_counter, 1);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= p.nq) break;
+        const int si = p.q[2 * qi], sj = p.q[2 * qi + 1];
+        for (int t = lane; t < FB_CAP; t += 32) { st.key[t] = FB_EMPTY; st.vis[t] = 0; }
+        __syncwarp();
+        uint32_t n = 0, peak = 0;
+        int ncells = 0, status = NSFS_OK;
+        long long pops = 0, expansions = 0, pushes = 0;
+        bool found = false;
+        uint32_t k_found = 0;
+        const uint32_t ks = (uint32_t)(si * W + sj);
+        if (si < 0 || si >= H || sj < 0 || sj >= W) status = NSFS_E_ARG;
+        else {
+            if (lane == 0) { const int s0 = fb_insert(st, ks); st.g[s0] = 0.0; }
+            ncells = 1;
+            __syncwarp();
+            heap_push(st.heap, n, make_entry(0.0, 0.0, ks, NSFS_MODE_G), prio, lane);
+            pushes = 1; peak = 1;
+        }
+        while (status == NSFS_OK && n > 0) {
+            const uint32_t ku = (uint32_t)(st.heap[1] & kKeyMask);
+            heap_pop(st.heap, n, prio, lane, ln);
+            pops++;
+            const int su = fb_find(st, ku);                    // every key on the open list is in the table
+            if (st.vis[su]) continue;                           // stale entry (djikstra.cpp:197-200)
+            __syncwarp();
+            if (lane == 0) st.vis[su] = 1;
+            expansions++;
+            if (bit_at(p.free_bits, ku)) { found = true; k_found = ku; break; }          // djikstra.cpp:205-211
+            const uint32_t om = __ldg(p.out_mask + ku);
+            if (om & kThrowBit) { status = NSFS_E_RANGE; break; }                        // vector::at throws (R6)
+            const int i = (int)(ku / uW);
+            const double gu = st.g[su];
+            uint32_t rowok = 0;                                 // directions whose row is in range (djikstra.cpp:222-226)
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int ni = i + nb_di(d);
+                if (ni >= 0 && ni < H) rowok |= 1u << d;
+            }
+            bool relax = false;
+            uint32_t kv = 0;
+            double cand = 0.0;
+            if (lane < 8 && ((rowok >> lane) & 1u)) {
+                const int d = lane;
+                kv = ku + (uint32_t)(nb_di(d) * W + nb_dj(d));
+                const int sv = fb_find(st, kv);
+                const double gv = sv >= 0 ? st.g[sv] : kInfD;
+                const bool card = !(__popc(rowok & ((1u << d) - 1u)) & 1);
+                if (!bit_at(p.free_bits, kv)) cand = bit_at(p.infl_bits, kv) ? __dadd_rn(gu, 100.0) : __dadd_rn(gu, 1000.0);   // djikstra.cpp:230-246
+                else cand = __dadd_rn(gu, card ? 1.0 : kSqrt2D);
+                relax = gv > __dadd_rn(cand, kSlack);
+            }
+            uint32_t rb = __ballot_sync(0xffffffffu, relax);
+            __syncwarp();
+            while (rb) {                                        // pushes in NB_LUT order
+                const int src = __ffs(rb) - 1;
+                rb &= rb - 1;
+                const uint32_t pk = __shfl_sync(0xffffffffu, kv, src);
+                const double pg = __shfl_sync(0xffffffffu, cand, src);
+                int sv = fb_find(st, pk);
+                if (sv < 0) {
+                    if (ncells >= FB_MAX_CELLS) { status = NSFS_E_HEAP; break; }
+                    if (lane == 0) fb_insert(st, pk);
+                    ncells++;
+                    __syncwarp();
+                    sv = fb_find(st, pk);
+                }
+                if (n >= (uint32_t)(FB_CAP - 2)) { status = NSFS_E_HEAP; break; }
+                if (lane == 0) st.g[sv] = pg;                  // the label changes even when the cell is closed (djikstra.cpp:255-259)
+                __syncwarp();
+                heap_push(st.heap, n, make_entry(pg, 0.0, pk, NSFS_MODE_G), prio, lane);
+                pushes++;
+                if (n > peak) peak = n;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const uint32_t kr = (found && status == NSFS_OK) ? k_found : ks;          // failure => the input cell (djikstra.cpp:272)
+            if (p.paths) { p.paths[2 * qi] = (int)(kr / uW); p.paths[2 * qi + 1] = (int)(kr % uW); }
+            if (p.status) p.status[qi] = status;
+            if (p.path_len) p.path_len[qi] = 1;
+            if (p.settled) p.settled[qi] = expansions;
+            if (p.stats5) {
+                atomicAdd((unsigned long long*)p.stats5 + 0, (unsigned long long)pops);
+                atomicAdd((unsigned long long*)p.stats5 + 1, (unsigned long long)expansions);
+                atomicAdd((unsigned long long*)p.stats5 + 2, (unsigned long long)pushes);
+                atomicMax((unsigned long long*)p.stats5 + 3, (unsigned long long)peak);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 int search_alloc(nsfs_planner* h, int want_slots) {
     SearchWork& s = h->search;
@@ -434,6 +573,30 @@ void search_free(nsfs_planner* h) {
     SearchWork& s = h->search;
     cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter);
     s = SearchWork();
+}
+
+// find_better_point on the shared-memory kernel: no per-query HBM state at all.
+int launch_fallback_small(nsfs_planner* h, int nq, const int32_t* d_q, int32_t* d_status, long long* d_settled, int32_t* d_cells,
+                          long long* d_stats5) {
+    if (nq <= 0) return NSFS_OK;
+    SearchWork& s = h->search;
+    if (!s.work_counter) NSFS_CUDA_TRY(h, cudaMalloc(&s.work_counter, sizeof(int)));
+    SearchParams p = {};
+    p.free_bits = h->d_free; p.infl_bits = h->d_inflated; p.out_mask = h->d_out_mask; p.work_counter = s.work_counter;
+    p.H = h->H; p.W = h->W; p.N = h->N; p.mode = NSFS_MODE_G;
+    p.nq = nq; p.q = d_q; p.status = d_status; p.settled = d_settled; p.paths = d_cells; p.path_cap = 1; p.stats5 = d_stats5;
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
+    const int block = SEARCH_WARPS_PER_BLOCK * 32;
+    long long warps = nq;
+    const long long cap = (long long)h->sm_count * 32;
+    if (warps > cap) warps = cap;
+    const int grid = (int)((warps + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK);
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+    fallback_small_kernel<<<grid, block, 0, h->stream>>>(p);
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
 }
 
 int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,

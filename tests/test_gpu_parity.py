@@ -184,3 +184,27 @@ def test_batch_kernel_agrees_with_wide_kernel(gpu_lib, spec):
     small = P.plan_batch(algo, mode, qs, path_cap=2048)
     assert np.array_equal(small["status"], wide["status"]) and np.array_equal(small["paths"], wide["paths"])
     P.close()
+
+
+@pytest.mark.gpu
+def test_fallback_in_shared_memory_agrees_with_the_wide_kernel(gpu_lib, oracle_mod):
+    """find_better_point normally runs with its whole state in shared memory (256-slot table, search.cu
+    fallback_small_kernel); searches that outgrow it are re-run on the wide kernel.  Same cells either way, and the
+    oracle's for a sample - including starts deep inside thick walls, which overflow the table."""
+    infl, lo = mapgen.synth_map(400, 360, 0.08, 91, inflated=True)
+    infl[150:190, 100:260] = 3; lo[150:190, 100:260] = 20          # a 40-cell-thick occupied slab
+    infl[250:270, 40:80] = 2                                         # an inflated-only block (cost +100 per cell)
+    bad = mapgen.sample_blocked_interior(infl, lo, 600, 91, margin=3)
+    bad = np.concatenate([bad, [[170, 180], [169, 181], [160, 120], [260, 60], [255, 45]]]).astype(np.int32)
+    P = gpu_lib.Planner(400, 360)
+    P.set_map(infl, lo)
+    small = P.find_better_point_batch(bad)
+    P.set_option("search_kernel", 1)
+    wide = P.find_better_point_batch(bad)
+    assert np.array_equal(small["cells"], wide["cells"]) and np.array_equal(small["status"], wide["status"])
+    assert (small["status"] == 0).sum() >= len(bad) - 3          # a start next to the frame may walk into a cell whose expansion throws
+    O = oracle_mod.Oracle(infl, lo)
+    for t in sorted(set(range(0, len(bad), 23)) | set(range(len(bad) - 5, len(bad))) | set(np.nonzero(small["status"])[0].tolist())):
+        o = O.find_better_point(bad[t])
+        assert small["status"][t] == o["status"] and tuple(small["cells"][t]) == o["cell"], t
+    P.close()
