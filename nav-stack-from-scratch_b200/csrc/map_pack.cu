@@ -54,10 +54,11 @@ __global__ void __launch_bounds__(256) pack_map_kernel(const int32_t* __restrict
 
 // ---- kernel 2: out-edge masks ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N,
-                                                       uint16_t* __restrict__ out_mask, long long k0, long long k1) {
-    const long long u = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= k1) return;
-    const int i = (int)(u / W);
+                                                       uint16_t* __restrict__ out_mask, int row0) {
+    // 2-D launch: blockIdx.y = row (no 64-bit division per cell), x = columns
+    const int i = row0 + (int)blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    const long long u = (long long)i * W + j;
     uint32_t pass = 0, diag = 0, thr = 0, card = 1;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
@@ -131,7 +132,9 @@ static int mask_range(nsfs_planner* h, long long k0, long long k1, long long j0,
     const int block = 256;
     const long long a_lo = (h->opt_active_row_lo > 0 ? h->opt_active_row_lo : 0) * (long long)h->W;
     const long long a_hi = h->opt_active_row_hi > 0 ? h->opt_active_row_hi * (long long)h->W : h->N;
-    if (k1 > k0) out_mask_kernel<<<(unsigned)((k1 - k0 + block - 1) / block), block, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, h->d_out_mask, k0, k1);
+    if (k1 > k0)       // whole rows (callers pass row-aligned ranges)
+        out_mask_kernel<<<dim3((unsigned)((h->W + block - 1) / block), (unsigned)((k1 - k0) / h->W)), block, 0, h->stream>>>(
+            h->d_free, h->H, h->W, h->N, h->d_out_mask, (int)(k0 / h->W));
     if (j1 > j0) in_mask_kernel<<<(unsigned)((j1 - j0 + block - 1) / block), block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, a_lo, a_hi, h->d_in_mask, j0, j1);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());
