@@ -25,6 +25,13 @@ namespace cg = cooperative_groups;
 
 namespace nsfs {
 
+#ifndef NSFS_FIELD_PROF
+#define NSFS_FIELD_PROF 0
+#endif
+#ifndef NSFS_FIELD_ORDERED
+#define NSFS_FIELD_ORDERED 1      // 0 = the first (flag-based, unordered) in-tile scheduler, kept for A/B measurements
+#endif
+
 #ifndef NSFS_TS
 #define NSFS_TS 64
 #endif
@@ -33,22 +40,18 @@ constexpr int SBW = 8, SBH = 4;        // sub-block: 8 columns x 4 rows = one la
 constexpr int SB_X = TS / SBW;
 constexpr int SB_Y = TS / SBH;
 constexpr int NSB = SB_X * SB_Y;       // sub-blocks per tile (128 / 32)
-constexpr int SB_PER_WARP = 4;         // warp w owns sub-blocks w, w + W, w + 2W, w + 3W (W = FIELD_WARPS)
+#ifndef NSFS_SB_PER_WARP
+#define NSFS_SB_PER_WARP 4
+#endif
+constexpr int SB_PER_WARP = NSFS_SB_PER_WARP;   // warp w owns sub-blocks w, w + Wn, w + 2 Wn, ... (Wn = FIELD_WARPS); 8 => two 512-thread blocks per SM
 constexpr int FIELD_WARPS = NSB / SB_PER_WARP;
 constexpr int FIELD_THREADS = FIELD_WARPS * 32;
 constexpr int FIELD_BLOCKS_PER_SM = 1024 / FIELD_THREADS;
-static_assert(FIELD_WARPS <= 32 && NSB % SB_PER_WARP == 0, "a warp polls its four flags as one word; the finisher reads one word per warp");
+static_assert(FIELD_WARPS <= 32 && NSB % SB_PER_WARP == 0 && (SB_PER_WARP == 4 || NSFS_FIELD_ORDERED), "the flag-based scheduler polls four flags as one word");
 constexpr int SROW = TS + 8;           // smem row stride in floats; SROW % 32 == 8 => the 4 rows of a sub-block use disjoint banks
 constexpr int SCOL0 = 4;               // smem column of tile column 0 (halo column -1 at 3)
 constexpr int SROWS = TS + 2;
 constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending update" (non-negative floats order like their bits)
-
-#ifndef NSFS_FIELD_PROF
-#define NSFS_FIELD_PROF 0
-#endif
-#ifndef NSFS_FIELD_ORDERED
-#define NSFS_FIELD_ORDERED 1      // 0 = the first (flag-based, unordered) in-tile scheduler, kept for A/B measurements
-#endif
 
 struct FieldParams {
     unsigned long long* prof;   // [8] cycle/iteration counters when NSFS_FIELD_PROF
@@ -226,8 +229,13 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     bool counted_idle = false;
     unsigned nap = p.wait_ns;                                         // idle back-off: short right after work, doubling up to idle_ns
     for (int spin = 0; spin < (1 << 26); ++spin) {
-        const uint32_t k0 = due[warp * 4 + 0], k1 = due[warp * 4 + 1], k2 = due[warp * 4 + 2], k3 = due[warp * 4 + 3];
-        const uint32_t mymin = min(min(k0, k1), min(k2, k3));
+        uint32_t mymin = kNoKey;
+        int q = 0;
+#pragma unroll
+        for (int qq = 0; qq < SB_PER_WARP; ++qq) {
+            const uint32_t kq = due[warp * SB_PER_WARP + qq];
+            if (kq < mymin) { mymin = kq; q = qq; }
+        }
         bool did = false;
         if (mymin != kNoKey) {
             uint32_t gmin = mymin;
@@ -238,22 +246,21 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                 gmin = min(mymin, __reduce_min_sync(0xffffffffu, g4));
             }
             if (__uint_as_float(mymin) <= __uint_as_float(gmin) + p.delta_in) {
-                const int q = mymin == k0 ? 0 : mymin == k1 ? 1 : mymin == k2 ? 2 : 3;
                 const int sb = warp + q * FIELD_WARPS;
                 if (counted_idle) {                                   // leave the idle count BEFORE consuming the key
                     if (lane == 0) atomicSub(s_ctl_, 1);
                     counted_idle = false;
                 }
                 __syncwarp();
-                if (lane == 0) atomicExch(s_due + warp * 4 + q, kNoKey);   // clear first, then read the neighbours
+                if (lane == 0) atomicExch(s_due + warp * SB_PER_WARP + q, kNoKey);   // clear first, then read the neighbours
                 __syncwarp();
-                const volatile float* c = s + soff[q];
                 // registers cannot be indexed by a run-time q: select
-                const uint32_t m = q == 0 ? mask[0] : q == 1 ? mask[1] : q == 2 ? mask[2] : mask[3];
-                float vq = q == 0 ? v[0] : q == 1 ? v[1] : q == 2 ? v[2] : v[3];
-                const int so = q == 0 ? soff[0] : q == 1 ? soff[1] : q == 2 ? soff[2] : soff[3];
+                uint32_t m = 0;
+                float vq = 0.f;
+                int so = 0;
+#pragma unroll
+                for (int qq = 0; qq < SB_PER_WARP; ++qq) if (qq == q) { m = mask[qq]; vq = v[qq]; so = soff[qq]; }
                 const volatile float* cc = s + so;
-                (void)c;
                 uint32_t bits = 0, last = 0;
                 float kchg = __uint_as_float(kNoKey);
                 for (int it = 0; it < p.inner; ++it) {
@@ -274,7 +281,8 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                     bits |= last;
                     __syncwarp();
                 }
-                if (q == 0) v[0] = vq; else if (q == 1) v[1] = vq; else if (q == 2) v[2] = vq; else v[3] = vq;
+#pragma unroll
+                for (int qq = 0; qq < SB_PER_WARP; ++qq) if (qq == q) v[qq] = vq;
                 if (bits) {
                     const uint32_t kmin = __reduce_min_sync(0xffffffffu, __float_as_uint(kchg));
                     __syncwarp();
@@ -452,6 +460,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     if (ASYNC_TILES && (p.peer_g[0] || p.peer_g[1])) __threadfence_system();   // ... also on the neighbour GPU
     else __threadfence();  // the improved cells are visible before the keys that announce them
     __syncthreads();
+    int newly = 0;        // tiles this thread made pending: summed over warp 0 and folded into ONE update of the pending counter
     if (ASYNC_TILES && tid >= 16 && tid < 32) {
         // wake the neighbour shard's tiles that hold, or read as halo, the two rows just pushed: its rows R-3 .. R+4 lie in at
         // most two tile rows; columns tx-1 .. tx+1 plus the far edge column when this tile touches a map edge (flat-key wrap)
@@ -467,7 +476,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
             if (cs == 3 && !dup) dup = abs(tcol - tx) <= 1;                // already covered by the three neighbour columns
             if (!dup) {
                 const uint32_t old = atomicMin(p.peer_key[side] + trow * p.tiles_x + tcol, m);
-                if (old > p.cap && m <= p.cap) atomicAdd(p.gcount, 1);
+                if (old > p.cap && m <= p.cap) newly = 1;
             }
         }
     }
@@ -494,8 +503,14 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         }
         if (target >= 0 && m != kNoKey) {
             const uint32_t old = atomicMin(p.tile_key + target, m);
-            if (ASYNC_TILES && old > p.cap && m <= p.cap) atomicAdd(p.gcount, 1);     // a tile became pending (within the cap)
+            if (ASYNC_TILES && old > p.cap && m <= p.cap) newly = 1;     // a tile became pending (within the cap)
         }
+    }
+    if (ASYNC_TILES && tid < 32) {
+        // the visit's net effect on "pending tiles + visits in flight": +newly pending, -1 for this visit.  One atomic, so the
+        // counter never dips below what is really outstanding and no second fence is needed before it.
+        const int net = __reduce_add_sync(0xffffffffu, newly) - 1;
+        if (tid == 0) s_ctl_[2] = net;
     }
     if (tid == 0) atomicAdd(p.counts + 3, 1);
 #if NSFS_FIELD_PROF
@@ -551,7 +566,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
     __shared__ __align__(16) uint32_t s_due[NSB];
-    __shared__ int s_ctl[2];
+    __shared__ int s_ctl[4];
     __shared__ uint32_t s_emin[16];
     __shared__ int s_int[2];
 
@@ -596,7 +611,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
     __shared__ float s[SROWS * SROW];
     __shared__ __align__(16) uint8_t s_flag[NSB];
     __shared__ __align__(16) uint32_t s_due[NSB];
-    __shared__ int s_ctl[2];
+    __shared__ int s_ctl[4];
     __shared__ uint32_t s_emin[16];
     __shared__ unsigned long long s_best;
     __shared__ uint32_t s_key;
@@ -659,10 +674,8 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         const float thr = fminf(__uint_as_float(my_key) + p.delta, __uint_as_float(p.cap));
         relax_tile<true>(p, tile, thr, s, s_flag, s_ctl, s_emin, s_due, my_key);
         if (tid == 0) {
-            __threadfence();
-            if (p.dynamic) atomicExch(p.tile_busy + tile, 0);
-            if (p.peer_g[0] || p.peer_g[1]) __threadfence_system();
-            atomicSub(p.gcount, 1);
+            if (p.dynamic) { __threadfence(); atomicExch(p.tile_busy + tile, 0); }
+            if (s_ctl[2] != 0) atomicAdd(p.gcount, s_ctl[2]);
         }
     }
 }
