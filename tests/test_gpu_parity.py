@@ -208,3 +208,22 @@ def test_fallback_in_shared_memory_agrees_with_the_wide_kernel(gpu_lib, oracle_m
         o = O.find_better_point(bad[t])
         assert small["status"][t] == o["status"] and tuple(small["cells"][t]) == o["cell"], t
     P.close()
+
+
+@pytest.mark.gpu
+def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
+    """The fp32 fixed point is unique, so the scheduling variants kept for A/B measurements (bulk-synchronous rounds with a
+    ballot-compacted tile list, dynamic tile claiming, other band widths) must agree bit for bit with the default."""
+    infl, lo = mapgen.synth_map(700, 900, 0.12, 93)
+    src = mapgen.field_source(infl, lo)
+    P = gpu_lib.Planner(700, 900)
+    P.set_map(infl, lo)
+    want = P.field(src)
+    for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_mode": 2, "field_groups": 1}, {"field_delta": 16}, {"field_delta": 100000},
+                 {"field_inner": 1}, {"field_delta_in": 8}):
+        for k in ("field_mode", "field_groups", "field_delta", "field_inner", "field_delta_in"):
+            P.set_option(k, opts.get(k, 0))
+        got = P.field(src)
+        assert got["status"] == 0 and np.array_equal(got["g"], want["g"]) and np.array_equal(got["pred"], want["pred"]), opts
+        assert got["reached"] == want["reached"]
+    P.close()
