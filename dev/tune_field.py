@@ -15,10 +15,11 @@ idles = [int(x) for x in os.environ.get('IDLES', '100').split(',')]
 alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
 dins = [int(x) for x in os.environ.get('DINS', '12').split(',')]
 groups = [int(x) for x in os.environ.get('TGROUPS', '0').split(',')]
+gates = [int(x) for x in os.environ.get('GATES', '0').split(',')]
 waits = [int(x) for x in os.environ.get('WAITS', '200').split(',')]
 for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, alphas, idles, dins, waits):
-  for grp in groups:
-    P.set_option('field_groups', grp)
+  for grp, gate in itertools.product(groups, gates):
+    P.set_option('field_groups', grp); P.set_option('field_gate', gate)
     P.set_option('field_delta_in', din); P.set_option('field_wait_ns', wait)
     P.set_option('field_idle_ns', idle)
     P.set_option('field_alpha', alpha)
@@ -31,4 +32,4 @@ for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, al
     g = P.field(src)['g']
     if ref is None: ref = g
     same = np.array_equal(ref, g)
-    print(f"groups {grp} din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)
+    print(f"gate {gate} groups {grp} din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)

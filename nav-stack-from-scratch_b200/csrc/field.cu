@@ -78,6 +78,8 @@ struct FieldParams {
     int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
     int peer_tiles_y[2];
     int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
+    uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
+    float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
     int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
     int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
     int dynamic;          // 1: any block takes the pending tile with the smallest key; 0: tile t belongs to block t % gridDim.x
@@ -639,7 +641,25 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
         for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
         if (lane == 0 && best != ~0ull) atomicMin(&s_best, best);
         __syncthreads();
-        const unsigned long long pick = s_best;
+        unsigned long long pick = s_best;
+        if (p.gate > 0.f) {
+            // global gate: publish my smallest pending key, read everybody's, and leave my tile alone if it is far ahead of the
+            // slowest part of the wavefront (it would only be relaxed against values that are still going to drop)
+            if (tid == 0) { __stcg(p.blk_min + blockIdx.x, (uint32_t)(pick >> 32)); s_key = kNoKey; }   // ~0ull >> 32 == kNoKey-or-larger: "nothing"
+            __syncthreads();
+            uint32_t gm = kNoKey;
+            for (int b = tid; b < (int)gridDim.x; b += FIELD_THREADS) gm = min(gm, __ldcg(p.blk_min + b));
+            gm = __reduce_min_sync(0xffffffffu, gm);
+            if (lane == 0 && gm < kNoKey) atomicMin(&s_key, gm);
+            __syncthreads();
+            const uint32_t gmin = s_key;
+            __syncthreads();
+            if (pick != ~0ull && gmin < kNoKey && __uint_as_float((uint32_t)(pick >> 32)) > __uint_as_float(gmin) + p.gate) {
+                if (++idle_spins > (1 << 22)) { if (tid == 0) atomicOr(p.counts + 4, 2); break; }
+                __nanosleep(200);
+                continue;
+            }
+        }
         if (pick == ~0ull) {
             int pending = 1;
             if (tid == 0) { pending = atomicAdd(p.gcount, 0); s_key = (uint32_t)pending; }
@@ -798,6 +818,8 @@ static FieldParams field_params(nsfs_planner* h) {
     FieldParams p;
     p.g = f.g; p.in_mask = h->d_in_mask; p.tile_key = f.tile_key; p.list = f.list[0];
     p.tile_busy = f.tile_busy;
+    p.blk_min = reinterpret_cast<uint32_t*>(f.list[0]);       // the bulk-synchronous variant's tile list is free in the asynchronous ones
+    p.gate = h->opt_field_gate > 0 ? (float)h->opt_field_gate : 0.f;
     p.gcount = f.counts + 1;
     for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; }
     p.own_lo = 0; p.own_hi = h->H;

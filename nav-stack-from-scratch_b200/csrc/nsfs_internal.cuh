@@ -113,6 +113,7 @@ struct nsfs_planner {
     long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
     long long opt_field_idle_ns = 0;    // 0 = default (100)
     long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
     long long opt_field_groups = 0;     // dynamic tile scheduling: tile groups (0 = default)
     long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
     long long opt_field_wait_ns = 0;    // ... back-off of a warp whose due sub-block is ahead of that band (0 = default 200)
