@@ -760,6 +760,8 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
+    if (!strcmp(key, "field_early")) { h->opt_field_early = value; return NSFS_OK; }
+    if (!strcmp(key, "field_merge")) { h->opt_field_merge = value; return NSFS_OK; }
     if (!strcmp(key, "field_gate")) { h->opt_field_gate = value; return NSFS_OK; }
     if (!strcmp(key, "field_groups")) { h->opt_field_groups = value; return NSFS_OK; }
     if (!strcmp(key, "field_delta_in")) { h->opt_field_delta_in = value; return NSFS_OK; }

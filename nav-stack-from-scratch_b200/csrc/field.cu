@@ -79,6 +79,8 @@ struct FieldParams {
     int peer_tiles_y[2];
     int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
     uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
+    int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
+    int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
     float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
     int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
     int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
@@ -194,7 +196,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     }
     if (tid < NSB) { s_flag[tid] = 1; s_due[tid] = key0; }            // first pass: everything is due (ordered: at the tile's own key)
     if (tid < 16) s_emin[tid] = kNoKey;                               // slot 11: this tile's own pending key; 12 / 13: peer shards
-    if (tid < 2) s_ctl[tid] = 0;
+    if (tid < 4) s_ctl[tid] = 0;                                      // 0 idle warps, 1 done, 2 net change of the pending counter, 3 merges
 
     // ---- this thread's four cells ---------------------------------------------------------------------
     const int lr = lane >> 3, lc = lane & 7;
@@ -298,6 +300,40 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                         if (need && sy >= 0 && sy < SB_Y && sx >= 0 && sx < SB_X)
                             atomicMin(s_due + (t % FIELD_WARPS) * SB_PER_WARP + t / FIELD_WARPS, kmin);
                     }
+                    if (ASYNC_TILES && p.early) {
+                        // cut-through between tiles: a changed cell that faces another tile is published NOW (value, fence, key)
+                        // instead of at the end of the visit, so the neighbouring tile starts on the wavefront while this one is
+                        // still relaxing; the end-of-visit posts to the 8 direct neighbours are then redundant and skipped
+                        const int sby = sb / SB_X, sbx = sb % SB_X;
+                        uint32_t outer = 0;
+                        if (sby == 0) outer |= bits & 0x000000ffu;
+                        if (sby == SB_Y - 1) outer |= bits & 0xff000000u;
+                        if (sbx == 0) outer |= bits & 0x01010101u;
+                        if (sbx == SB_X - 1) outer |= bits & 0x80808080u;
+                        if (outer) {
+                            if ((outer >> lane) & 1u) {
+                                int gk = -1;
+#pragma unroll
+                                for (int qq = 0; qq < SB_PER_WARP; ++qq) if (qq == q) gk = key[qq];
+                                if (gk >= 0) __stcg(p.g + gk, vq);
+                            }
+                            __threadfence();
+                            __syncwarp();
+                            if (lane < 9 && lane != 4) {
+                                const int dy = lane / 3 - 1, dx = lane % 3 - 1;
+                                uint32_t need = bits;
+                                if (dy < 0) need &= 0x000000ffu; else if (dy > 0) need &= 0xff000000u;
+                                if (dx < 0) need &= 0x01010101u; else if (dx > 0) need &= 0x80808080u;
+                                const int sy = sby + dy, sx = sbx + dx;
+                                const int tdy = sy < 0 ? -1 : (sy >= SB_Y ? 1 : 0), tdx = sx < 0 ? -1 : (sx >= SB_X ? 1 : 0);
+                                const int ny = ty + tdy, nx = tx + tdx;
+                                if (need && (tdy || tdx) && ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
+                                    const uint32_t old = atomicMin(p.tile_key + ny * p.tiles_x + nx, kmin);
+                                    if (old > p.cap && kmin <= p.cap) atomicAdd(p.gcount, 1);
+                                }
+                            }
+                        }
+                    }
                 }
                 did = true;
                 nap = p.wait_ns;
@@ -317,7 +353,52 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
 #pragma unroll
                 for (int t = 0; t < NSB / 32; ++t) g4 = min(g4, due[lane + 32 * t]);
                 const bool any = __any_sync(0xffffffffu, g4 != kNoKey);
-                if (!any && s_ctl[0] == FIELD_WARPS && lane == 0) s_ctl[1] = 1;
+                if (!any && s_ctl[0] == FIELD_WARPS) {
+                    // Before ending the visit: did a neighbour post to THIS tile meanwhile (within the band)?  Then stay on it:
+                    // take the key, re-read the halo ring, wake the sub-blocks next to halo cells that dropped.  Saves the
+                    // publish / claim / stage round trip of a separate visit, which sits on the wavefront's critical path.
+                    uint32_t pk = kNoKey;
+                    if (ASYNC_TILES && p.merge) {
+                        if (lane == 0) {
+                            pk = __ldcg(p.tile_key + tile);
+                            pk = (pk <= __float_as_uint(thr) && pk <= p.cap) ? atomicExch(p.tile_key + tile, kNoKey) : kNoKey;
+                            if (pk != kNoKey) {
+                                __threadfence();
+                                s_ctl_[3] += 1;                       // two counted units (pending + in flight) become one
+                                atomicSub(s_ctl_, 1);                 // I am busy again: nobody else can end the visit while I refresh the halo
+                            }
+                        }
+                        pk = __shfl_sync(0xffffffffu, pk, 0);
+                    }
+                    if (pk != kNoKey) {
+                        counted_idle = false;
+                        for (int hx = lane; hx < 4 * TS + 4; hx += 32) {
+                            int rr, cc;                                       // position on the ring of the (TS+2)^2 staged square
+                            if (hx < TS + 2) { rr = 0; cc = hx; }
+                            else if (hx < 2 * (TS + 2)) { rr = TS + 1; cc = hx - (TS + 2); }
+                            else if (hx < 2 * (TS + 2) + TS) { rr = hx - 2 * (TS + 2) + 1; cc = 0; }
+                            else { rr = hx - 2 * (TS + 2) - TS + 1; cc = TS + 1; }
+                            const long long gk = (long long)(r0 - 1 + rr) * W + (c0 - 1 + cc);
+                            if (gk < 0 || gk >= N) continue;
+                            const float nv = __ldcg(p.g + gk);
+                            const int so2 = rr * SROW + (SCOL0 - 1) + cc;
+                            if (nv < s[so2]) {
+                                s[so2] = nv;
+                                // interior cells within one step of the halo cell: rows rr-2 .. rr, columns cc-2 .. cc (tile coordinates)
+                                const int y0 = max(rr - 2, 0), y1 = min(rr, TS - 1), x0 = max(cc - 2, 0), x1 = min(cc, TS - 1);
+                                const uint32_t kb = __float_as_uint(nv);
+                                for (int yy = 0; yy < 2; ++yy)
+                                    for (int xx = 0; xx < 2; ++xx) {
+                                        const int t2 = ((yy ? y1 : y0) / SBH) * SB_X + (xx ? x1 : x0) / SBW;
+                                        atomicMin(s_due + (t2 % FIELD_WARPS) * SB_PER_WARP + t2 / FIELD_WARPS, kb);
+                                    }
+                            }
+                        }
+                        __syncwarp();
+                        continue;                                     // poll again: my own sub-blocks may be due; idle + finisher check come after
+                    }
+                    if (lane == 0) s_ctl[1] = 1;
+                }
             }
         }
         if (s_ctl[1]) break;
@@ -490,7 +571,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         if (tid < 9 && tid != 4) {
             const int ny = ty + tid / 3 - 1, nx = tx + tid % 3 - 1;
             m = s_emin[tid];
-            if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) target = ny * p.tiles_x + nx;
+            if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x && !(ASYNC_TILES && p.early)) target = ny * p.tiles_x + nx;
         } else if (tid >= 9 && tid < 12) {
             const int ny = ty + (tid - 10);
             m = s_emin[9];
@@ -511,7 +592,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     if (ASYNC_TILES && tid < 32) {
         // the visit's net effect on "pending tiles + visits in flight": +newly pending, -1 for this visit.  One atomic, so the
         // counter never dips below what is really outstanding and no second fence is needed before it.
-        const int net = __reduce_add_sync(0xffffffffu, newly) - 1;
+        const int net = __reduce_add_sync(0xffffffffu, newly) - 1 - s_ctl_[3];
         if (tid == 0) s_ctl_[2] = net;
     }
     if (tid == 0) atomicAdd(p.counts + 3, 1);
@@ -820,6 +901,8 @@ static FieldParams field_params(nsfs_planner* h) {
     p.tile_busy = f.tile_busy;
     p.blk_min = reinterpret_cast<uint32_t*>(f.list[0]);       // the bulk-synchronous variant's tile list is free in the asynchronous ones
     p.gate = h->opt_field_gate > 0 ? (float)h->opt_field_gate : 0.f;
+    p.early = h->opt_field_early == 2 ? 0 : 1;                // 0 / 1 = on (default), 2 = off
+    p.merge = h->opt_field_merge == 2 ? 0 : 1;
     p.gcount = f.counts + 1;
     for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; }
     p.own_lo = 0; p.own_hi = h->H;
@@ -922,6 +1005,8 @@ int launch_field_relax_p2p(nsfs_planner* h) {
     if (f.own_hi > f.own_lo) { p.own_lo = f.own_lo; p.own_hi = f.own_hi; }
     p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
     p.dynamic = 0;
+    p.merge = 0;
+    p.early = 0;            // ghost rows are lowered with atomics by both sides; keep their publication at the end of the visit
     int per_sm = 0;
     NSFS_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_solve_async_kernel, FIELD_THREADS, 0));
     if (per_sm < 1) return set_cuda_error(h, cudaErrorLaunchOutOfResources, "field_solve_async_kernel occupancy");

@@ -113,6 +113,8 @@ struct nsfs_planner {
     long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
     long long opt_field_idle_ns = 0;    // 0 = default (100)
     long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    long long opt_field_early = 0;      // post border changes to neighbouring tiles during a visit (cut-through): 0 / 1 = on, 2 = off
+    long long opt_field_merge = 0;      // a visit absorbs posts that arrive for its own tile before it ends: 0 / 1 = on, 2 = off
     long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
     long long opt_field_groups = 0;     // dynamic tile scheduling: tile groups (0 = default)
     long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
