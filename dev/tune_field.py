@@ -16,8 +16,9 @@ alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
 dins = [int(x) for x in os.environ.get('DINS', '12').split(',')]
 groups = [int(x) for x in os.environ.get('TGROUPS', '0').split(',')]
 gates = [int(x) for x in os.environ.get('GATES', '0').split(',')]
-P.set_option('field_early', int(os.environ.get('EARLY', '0'))  # 0/1 on, 2 off)
-P.set_option('field_merge', int(os.environ.get('MERGE', '0'))  # 0/1 on, 2 off)
+P.set_option('field_early', int(os.environ.get('EARLY', '0')))   # 0/1 on, 2 off
+P.set_option('field_sched_ns', int(os.environ.get('SCHED', '0')))
+P.set_option('field_merge', int(os.environ.get('MERGE', '0')))   # 0/1 on, 2 off
 waits = [int(x) for x in os.environ.get('WAITS', '200').split(',')]
 for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, alphas, idles, dins, waits):
   for grp, gate in itertools.product(groups, gates):

@@ -762,6 +762,7 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_early")) { h->opt_field_early = value; return NSFS_OK; }
     if (!strcmp(key, "field_merge")) { h->opt_field_merge = value; return NSFS_OK; }
+    if (!strcmp(key, "field_sched_ns")) { h->opt_field_sched_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_gate")) { h->opt_field_gate = value; return NSFS_OK; }
     if (!strcmp(key, "field_groups")) { h->opt_field_groups = value; return NSFS_OK; }
     if (!strcmp(key, "field_delta_in")) { h->opt_field_delta_in = value; return NSFS_OK; }

@@ -79,6 +79,7 @@ struct FieldParams {
     int peer_tiles_y[2];
     int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
     uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
+    unsigned sched_ns;    // back-off of a block that owns no pending tile
     int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
     int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
     float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(FIELD_THREADS, FIELD_BLOCKS_PER_SM) field_solv
             __syncthreads();
             if (pending <= 0) break;
             if (++idle_spins > (1 << 22)) { if (tid == 0) atomicOr(p.counts + 4, 2); break; }
-            __nanosleep(400);
+            __nanosleep(p.sched_ns);
             continue;
         }
         idle_spins = 0;
@@ -903,6 +904,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.gate = h->opt_field_gate > 0 ? (float)h->opt_field_gate : 0.f;
     p.early = h->opt_field_early == 2 ? 0 : 1;                // 0 / 1 = on (default), 2 = off
     p.merge = h->opt_field_merge == 2 ? 0 : 1;
+    p.sched_ns = h->opt_field_sched_ns > 0 ? (unsigned)h->opt_field_sched_ns : 400u;
     p.gcount = f.counts + 1;
     for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; }
     p.own_lo = 0; p.own_hi = h->H;
@@ -913,7 +915,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.counts = f.counts; p.H = h->H; p.W = h->W; p.N = h->N; p.tiles_x = f.tiles_x; p.tiles_y = f.tiles_y;
     p.max_rounds = 1 << 30;
     p.prof = nullptr;
-    p.inner = h->opt_field_inner > 0 ? (int)h->opt_field_inner : 8;
+    p.inner = h->opt_field_inner > 0 ? (int)h->opt_field_inner : 16;
     p.idle_ns = h->opt_field_idle_ns > 0 ? (unsigned)h->opt_field_idle_ns : 1000u;
     p.delta = h->opt_field_delta > 0 ? (float)h->opt_field_delta : 128.0f;
     p.alpha = h->opt_field_alpha >= 0 ? (float)h->opt_field_alpha / 100.0f : 0.5f;

@@ -108,13 +108,14 @@ struct nsfs_planner {
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
-    long long opt_field_inner = 0;      // 0 = default (4)
-    long long opt_field_delta = 0;      // 0 = default (64)
+    long long opt_field_inner = 0;      // 0 = default (16)
+    long long opt_field_delta = 0;      // 0 = default (128)
     long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
-    long long opt_field_idle_ns = 0;    // 0 = default (100)
-    long long opt_field_alpha = -1;     // percent; < 0 = default (100)
+    long long opt_field_idle_ns = 0;    // 0 = default (1000)
+    long long opt_field_alpha = -1;     // percent; < 0 = default (50); bulk-synchronous variant only
     long long opt_field_early = 0;      // post border changes to neighbouring tiles during a visit (cut-through): 0 / 1 = on, 2 = off
     long long opt_field_merge = 0;      // a visit absorbs posts that arrive for its own tile before it ends: 0 / 1 = on, 2 = off
+    long long opt_field_sched_ns = 0;   // back-off of a block with no pending tile (0 = default 400)
     long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
     long long opt_field_groups = 0;     // dynamic tile scheduling: tile groups (0 = default)
     long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
