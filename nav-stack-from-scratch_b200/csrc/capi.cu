@@ -503,12 +503,13 @@ int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, 
 }
 
 static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches0, float ms, float main_ms) {
-    int counts[8];
+    int counts[16];
     NSFS_CUDA_TRY(h, cudaMemcpyAsync(counts, h->field.counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (st) {
         memset(st, 0, sizeof(*st));
         st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5];
+        st->pops = counts[8]; st->pushes = counts[9]; st->heap_peak = counts[10];   // bucket kernel: steps, merged posts, empty visits
         st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
     }
     if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }

@@ -51,52 +51,15 @@ static_assert(FIELD_WARPS <= 32 && NSB % SB_PER_WARP == 0 && (SB_PER_WARP == 4 |
 constexpr int SROW = TS + 8;           // smem row stride in floats; SROW % 32 == 8 => the 4 rows of a sub-block use disjoint banks
 constexpr int SCOL0 = 4;               // smem column of tile column 0 (halo column -1 at 3)
 constexpr int SROWS = TS + 2;
-constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending update" (non-negative floats order like their bits)
 
-struct FieldParams {
-    unsigned long long* prof;   // [8] cycle/iteration counters when NSFS_FIELD_PROF
-    float* g;
-    const uint16_t* in_mask;
-    uint32_t* tile_key;   // per tile: smallest value a neighbour wrote into this tile's halo since it was last relaxed
-    int* list;
-    int* counts;          // 0: list length; 2: rounds; 3: tile visits; 4: error flag; 5: reached; 6: sweeps
-    int H, W;
-    long long N;
-    int tiles_x, tiles_y;
-    int max_rounds;
-    unsigned idle_ns;     // back-off of a warp that has nothing to relax
-    int inner;            // warp-local relaxations of an active sub-block per block-wide sweep
-    float delta;          // width of the cost band [.., thr] the wavefront may advance into per round (delta-stepping)
-    float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
-    float delta_in;       // ordered relaxation: a sub-block runs while its key is within delta_in of the tile's smallest due key
-    unsigned wait_ns;     // ... and otherwise waits this long before looking again
-    // peer-to-peer shards (NVLink): side 0 = the shard above (smaller rows), 1 = below.  A shard pushes every improvement
-    // of its first / last two OWNED rows straight into the neighbour's ghost rows and wakes the neighbour's tiles.
-    int* gcount;          // pending tiles + visits in flight: counts + 1, or ONE counter shared by all shards (on the owner's GPU)
-    float* peer_g[2];     // the neighbour's g array (its local rows), nullptr = no neighbour on that side
-    uint32_t* peer_key[2];
-    int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
-    int peer_tiles_y[2];
-    int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
-    uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
-    unsigned sched_ns;    // back-off of a block that owns no pending tile
-    int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
-    int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
-    float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
-    int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
-    int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
-    int dynamic;          // 1: any block takes the pending tile with the smallest key; 0: tile t belongs to block t % gridDim.x
-    uint32_t cap;         // float bits: tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it
-                          // (kNoKey - 1 = no cap).  Used by the multi-GPU solve to advance all shards band by band.
-};
 
-__global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* __restrict__ g, long long N,
-                                  uint32_t* __restrict__ tile_key, int* __restrict__ tile_busy, int n_tiles) {
+__global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* __restrict__ g, float4* __restrict__ gx4, float* __restrict__ gx,
+                                  long long N, uint32_t* __restrict__ tile_key, int* __restrict__ tile_busy, int n_tiles) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float4 v = make_float4(kInfF, kInfF, kInfF, kInfF);
-    for (long long k = t; k < n4; k += stride) g4[k] = v;
-    for (long long k = n4 * 4 + t; k < N; k += stride) g[k] = kInfF;
+    for (long long k = t; k < n4; k += stride) { g4[k] = v; gx4[k] = v; }     // gx: "never expanded" (field_bucket.cu)
+    for (long long k = n4 * 4 + t; k < N; k += stride) { g[k] = kInfF; gx[k] = kInfF; }
     for (long long k = t; k < n_tiles; k += stride) { tile_key[k] = kNoKey; tile_busy[k] = 0; }
 }
 
@@ -106,7 +69,7 @@ __global__ void field_seed_kernel(FieldParams p, const uint32_t* __restrict__ fr
                                   const uint16_t* __restrict__ out_mask, int si, int sj) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (si < 0) {                               // no source on this shard: everything arrives through field_inject_kernel
-        for (int c = 0; c < 8; ++c) p.counts[c] = 0;
+        for (int c = 0; c < 16; ++c) p.counts[c] = 0;
         p.counts[7] = __float_as_int(-1e30f);
         return;
     }
@@ -130,7 +93,7 @@ __global__ void field_seed_kernel(FieldParams p, const uint32_t* __restrict__ fr
             seed_tile(tile_of(kv));
         }
     }
-    for (int c = 0; c < 8; ++c) p.counts[c] = 0;
+    for (int c = 0; c < 16; ++c) p.counts[c] = 0;
     p.counts[1] = pend;                        // asynchronous scheduler: pending tiles + visits in flight
     p.counts[7] = __float_as_int(-1e30f);      // previous round's threshold
 }
@@ -886,6 +849,7 @@ int field_alloc(nsfs_planner* h) {
     f.tiles_y = (h->H + TS - 1) / TS;
     const int n_tiles = f.tiles_x * f.tiles_y;
     NSFS_CUDA_TRY(h, cudaMalloc(&f.g, (size_t)(h->N + 4) * sizeof(float)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&f.gx, (size_t)(h->N + 4) * sizeof(float)));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.pred, (size_t)h->N));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.tile_key, (size_t)(n_tiles + 32) * sizeof(uint32_t)));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.list[0], (size_t)(n_tiles + 32) * sizeof(int)));
@@ -896,14 +860,14 @@ int field_alloc(nsfs_planner* h) {
 
 void field_free(nsfs_planner* h) {
     FieldWork& f = h->field;
-    cudaFree(f.g); cudaFree(f.pred); cudaFree(f.tile_key); cudaFree(f.list[0]); cudaFree(f.tile_busy); cudaFree(f.counts);
+    cudaFree(f.g); cudaFree(f.gx); cudaFree(f.pred); cudaFree(f.tile_key); cudaFree(f.list[0]); cudaFree(f.tile_busy); cudaFree(f.counts);
     f = FieldWork();
 }
 
 static FieldParams field_params(nsfs_planner* h) {
     FieldWork& f = h->field;
     FieldParams p;
-    p.g = f.g; p.in_mask = h->d_in_mask; p.tile_key = f.tile_key; p.list = f.list[0];
+    p.g = f.g; p.gx = f.gx; p.out_mask = h->d_out_mask; p.win_lo = 0; p.win_hi = h->N; p.in_mask = h->d_in_mask; p.tile_key = f.tile_key; p.list = f.list[0];
     p.tile_busy = f.tile_busy;
     p.blk_min = reinterpret_cast<uint32_t*>(f.list[0]);       // the bulk-synchronous variant's tile list is free in the asynchronous ones
     p.gate = h->opt_field_gate > 0 ? (float)h->opt_field_gate : 0.f;
@@ -941,7 +905,8 @@ int launch_field_begin(nsfs_planner* h, int si, int sj) {
     long long fill_blocks = (n4 + 255) / 256;
     if (fill_blocks < 1) fill_blocks = 1;
     if (fill_blocks > (long long)h->sm_count * 8) fill_blocks = (long long)h->sm_count * 8;
-    field_fill_kernel<<<(int)fill_blocks, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, h->N, f.tile_key, f.tile_busy, f.tiles_x * f.tiles_y);
+    field_fill_kernel<<<(int)fill_blocks, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, reinterpret_cast<float4*>(f.gx), f.gx, h->N, f.tile_key,
+                                                              f.tile_busy, f.tiles_x * f.tiles_y);
     field_seed_kernel<<<1, 32, 0, h->stream>>>(p, h->d_free, h->d_out_mask, si, sj);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());
@@ -974,6 +939,14 @@ int launch_field_relax(nsfs_planner* h, float cap) {
     cudaMemsetAsync(d_prof, 0, 8 * 4100, h->stream);
     p.prof = d_prof;
 #endif
+    if (h->opt_field_mode == 3) {      // bucketed push expansion (field_bucket.cu)
+        int rc = launch_field_relax_bucket(h, p);
+        if (rc != NSFS_OK) return rc;
+        field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);
+        h->launches++;
+        NSFS_CUDA_TRY(h, cudaGetLastError());
+        return NSFS_OK;
+    }
     int per_sm = 0;
     const bool async_tiles = h->opt_field_mode != 1;
     NSFS_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, async_tiles ? field_solve_async_kernel : field_solve_kernel, FIELD_THREADS, 0));

@@ -32,8 +32,53 @@ constexpr float  kSqrt2F = 1.41421356237309504880f;
 // in_mask[v]  (uint16): bits 0..7  in-edge d exists from the FREE cell v-OFF[d]; bits 8..15 it costs sqrt(2)
 constexpr uint32_t kThrowBit = 1u << 8;
 
+constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending update" (non-negative floats order like their bits)
+constexpr int kFieldTile = 64;              // tile side of the field solvers (field.cu, field_bucket.cu)
+
+// Parameters of the field solve kernels (field.cu: pull relaxation; field_bucket.cu: bucketed push expansion).
+struct FieldParams {
+    unsigned long long* prof;   // [8] cycle/iteration counters when NSFS_FIELD_PROF
+    float* g;
+    float* gx;            // bucket kernel: the value each cell was last expanded at (g < gx: the cell is open)
+    const uint16_t* out_mask;
+    long long win_lo, win_hi;   // bucket kernel: cells outside [win_lo, win_hi) take no in-edges (row-partitioned shards)
+    const uint16_t* in_mask;
+    uint32_t* tile_key;   // per tile: smallest value a neighbour wrote into this tile's halo since it was last relaxed
+    int* list;
+    int* counts;          // 0: list length; 2: rounds; 3: tile visits; 4: error flag; 5: reached; 6: sweeps
+    int H, W;
+    long long N;
+    int tiles_x, tiles_y;
+    int max_rounds;
+    unsigned idle_ns;     // back-off of a warp that has nothing to relax
+    int inner;            // warp-local relaxations of an active sub-block per block-wide sweep
+    float delta;          // width of the cost band [.., thr] the wavefront may advance into per round (delta-stepping)
+    float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
+    float delta_in;       // ordered relaxation: a sub-block runs while its key is within delta_in of the tile's smallest due key
+    unsigned wait_ns;     // ... and otherwise waits this long before looking again
+    // peer-to-peer shards (NVLink): side 0 = the shard above (smaller rows), 1 = below.  A shard pushes every improvement
+    // of its first / last two OWNED rows straight into the neighbour's ghost rows and wakes the neighbour's tiles.
+    int* gcount;          // pending tiles + visits in flight: counts + 1, or ONE counter shared by all shards (on the owner's GPU)
+    float* peer_g[2];     // the neighbour's g array (its local rows), nullptr = no neighbour on that side
+    uint32_t* peer_key[2];
+    int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
+    int peer_tiles_y[2];
+    int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
+    uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
+    unsigned sched_ns;    // back-off of a block that owns no pending tile
+    int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
+    int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
+    float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
+    int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
+    int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
+    int dynamic;          // 1: any block takes the pending tile with the smallest key; 0: tile t belongs to block t % gridDim.x
+    uint32_t cap;         // float bits: tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it
+                          // (kNoKey - 1 = no cap).  Used by the multi-GPU solve to advance all shards band by band.
+};
+
 struct FieldWork {
     float*    g = nullptr;         // [N]
+    float*    gx = nullptr;        // [N] bucket kernel: value at the last expansion (1e5 = never)
     uint8_t*  pred = nullptr;      // [N]
     uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
     int*      list[2] = {nullptr, nullptr};
@@ -141,6 +186,7 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
 int launch_field_begin(nsfs_planner* h, int si, int sj);
 int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved);
 int launch_field_relax(nsfs_planner* h, float cap);
+int launch_field_relax_bucket(nsfs_planner* h, FieldParams p);
 int launch_field_relax_p2p(nsfs_planner* h);
 int launch_field_count_pending(nsfs_planner* h);
 int launch_field_finish(nsfs_planner* h);
