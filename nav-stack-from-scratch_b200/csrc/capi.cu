@@ -1,5 +1,6 @@
 // extern "C" surface of libnsfs_gpu.so (include/nsfs.h): argument checks, staging copies, launches, results.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -512,6 +513,9 @@ static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches
         st->pops = counts[8]; st->pushes = counts[9]; st->heap_peak = counts[10];   // bucket kernel: steps, merged posts, empty visits
         st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
     }
+    if (getenv("NSFS_FIELD_DEBUG"))
+        fprintf(stderr, "[field] visits %d steps %d rounds %d merges %d empty %d | cycles/16: stage %d loop %d end %d end-wait %d\n", counts[3], counts[8], counts[14],
+                counts[9], counts[10], counts[11], counts[12], counts[13], counts[15]);
     if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }
     uint32_t kb = (uint32_t)counts[6];                  // smallest key still pending (float bits; +inf bits = none)
     memcpy(&h->field.min_pending, &kb, sizeof(kb));

@@ -1,28 +1,32 @@
-// Djikstra cost-to-go field, bucketed push expansion (field_mode 3): the in-tile solver that replaces the pull
-// relaxation of field.cu where it applies (one GPU, or row-partitioned shards driven in rounds).
+// Djikstra cost-to-go field, bucket-ordered tile solver (field_mode 3): the in-tile schedule that replaces the
+// asynchronous pull relaxation of field.cu where it applies (one GPU, or row-partitioned shards driven in rounds).
 //
 // Same result as field.cu (the unique fp32 fixed point of g[v] = min_u g[u] + w(u, v) on the reference's quirk graph,
 // djikstra.cpp:27-145 / SURVEY.md R13), different schedule.  The reference's open list is keyed on (int)g and every edge
-// costs >= 1, so all cells of one integer bucket [b, b+1) can be expanded together once the buckets below are done
+// costs >= 1, so all cells of one integer bucket [b, b+1) can be settled together once the buckets below are done
 // (delta-stepping with delta = 1 = the smallest edge weight: no light edges, one pass per bucket).  A tile visit is
-// therefore a label-SETTING sweep over buckets, each cell expanded once per visit, instead of a label-correcting
-// relaxation that re-reads 8 neighbours per cell per pass:
+// therefore a label-SETTING sweep over buckets: a cell is pulled when it is due, settled once, and tells its
+// out-neighbours when THEY are due, instead of a label-correcting relaxation that re-reads 8 neighbours per cell per pass.
 //
 //   * 64x64 tile + 1-cell halo in shared memory, addressed by FLAT key (the reference's column wrap comes for free);
-//     per cell: g (fp32), the 16-bit out-edge mask of map_pack.cu, one state byte (open / touched).
-//   * 128 bucket lists of 16-bit cell ids; a bit map of the non-empty ones.  One step = one barrier among the 256
-//     worker threads: find the lowest non-empty bucket, one thread per entry, 8 shared-memory atomicMin pushes, append
-//     the lowered neighbours to the lists of buckets b+1 / b+2 (__ffs over the bit map picks the next bucket).
-//   * edges that leave the tile lower the halo copy and mark it dirty; a ninth "courier" warp owns ALL global-memory
-//     traffic during the visit: it drains dirty halo cells (atomicMin into g, fence, key post to the target tile), and
-//     polls the tile's own key: when a neighbour has lowered border cells of this tile meanwhile, the courier reads the
-//     border and hands the lower values to the workers through an inbox.  The workers never wait on HBM / L2.
+//     per position: g (fp32) and the 16-bit in-edge mask of map_pack.cu; per cell a DUE byte (0 = nothing to do,
+//     1 + bucket the cell has to be looked at in) and a state byte (open / touched).
+//   * no atomics on the tile's own cells ("owner computes"): thread t owns the 16 due bytes of cells 16t .. 16t+15 and
+//     reads them with one 128-bit load per step; the cells due in the current bucket are compacted into the warp's
+//     work list, pulled (8 shared loads, min tree), settled by a plain store, and their out-neighbours that would
+//     improve get their due byte set by a plain byte store.  One named barrier per bucket among the 256 workers.
+//   * edges that leave the tile lower the halo copy (shared atomicMin: several border cells may feed one halo cell) and
+//     mark it dirty; a ninth "courier" warp owns ALL global-memory traffic during the visit: it drains dirty halo cells
+//     (atomicMin into g, fence, key post to the target tile) and polls the tile's own key: when a neighbour has lowered
+//     border cells of this tile meanwhile, the courier reads the border and hands the lower values to the workers
+//     through an inbox.  The workers never wait on HBM / L2.
 //   * between visits a cell is "open" iff g < gx, gx = the value it was last expanded at (a second fp32 plane), so a visit
 //     knows what is left to expand from the planes alone: whoever lowers g[v] only has to post the tile key.
 //
 // Tile scheduling between visits is the asynchronous scheme of field.cu: tile t belongs to block t % gridDim.x, a block
 // takes its pending tile with the smallest key; counts[1] = pending tiles + visits in flight ends the kernel.
 #include <cstdio>
+#include <cstdlib>
 
 #include "nsfs_internal.cuh"
 
@@ -36,19 +40,23 @@ constexpr int B_SCOL0 = 4;                      // smem column of tile column 0 
 constexpr int B_SROWS = BT + 2;
 constexpr int B_POS = B_SROWS * B_SROW;         // staged positions (4752)
 constexpr int B_HDW = (B_POS + 31) / 32;        // words of the dirty-halo bit map
-constexpr int B_NB = 128;                       // bucket slots of a visit: [B0, B0 + B_NB)
-constexpr int B_CAP = 144;                      // entries per bucket list; beyond: the bucket is found by a tile scan
+constexpr int B_MAXBAND = 250;                  // due bytes hold 1 + (bucket - B0)
 constexpr int B_WORKERS = 256;
+constexpr int B_WARPS = B_WORKERS / 32;
 constexpr int B_THREADS = B_WORKERS + 32;       // + the courier warp
 constexpr int B_CREDIT = 16;                    // a visit in flight counts 1 + B_CREDIT: covers key posts not yet accounted
 constexpr int B_OUTCAP = 320;
 constexpr int kIn = 1, kStop = 2, kEnd = 4;
-static_assert(B_CAP <= B_WORKERS && B_NB % 32 == 0 && B_NB / 32 == 4, "one worker per list entry; the bit map is one uint4");
+static_assert(B_WORKERS * 16 == BT * BT, "one worker per 16 due bytes");
 
 struct __align__(16) BucketSmem {
     float g[B_POS];
-    uint32_t nonempty[B_NB / 32];
-    int cnt[B_NB];
+    uint16_t im[B_POS];
+    uint8_t due[BT * BT];    // 0 = idle, else 1 + (bucket - B0) the cell is due in
+    uint8_t st[BT * BT];     // bit 0: open (lowered / re-opened, not expanded at its value); bit 1: touched in this visit (write back)
+    uint16_t wl[B_WARPS][512];
+    int wcnt[2][B_WARPS];
+    int wmin[2][B_WARPS];
     uint32_t hdirty[B_HDW + 3];
     uint32_t inbox_val[256];
     uint32_t post_min[16];
@@ -58,63 +66,90 @@ struct __align__(16) BucketSmem {
     int want_end;
     int in_cnt;
     int out_cnt;
-    int B0;
-    int smax;
     uint32_t red_min;
     uint32_t key;
     unsigned long long best;
     uint16_t inbox_cell[256];
     uint16_t out_list[B_OUTCAP];
-    uint16_t om[BT * BT];
-    uint16_t list[B_NB * B_CAP];
-    uint8_t st[BT * BT];     // bit 0: open (lowered, not expanded at its value); bit 1: touched in this visit (write back)
-    uint8_t ovf[B_NB];
 };
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(B_WORKERS) : "memory"); }
 
-__device__ __forceinline__ int cell_pos(int c) { return ((c >> 6) + 1) * B_SROW + B_SCOL0 + (c & 63); }
+// Cell ids interleave the rows over the warps (warp w owns the due bytes of cells 512w .. 512w+511 = tile rows w, w+8, w+16, ...),
+// so a wavefront crossing the tile spreads its cells over all eight work lists.  Row <-> id row: swap the two 3-bit halves.
+__device__ __forceinline__ int row_swap(int r) { return ((r & 7) << 3) | (r >> 3); }
+__device__ __forceinline__ int cell_of(int ly, int lx) { return (row_swap(ly) << 6) | lx; }
+__device__ __forceinline__ int cell_row(int c) { return row_swap(c >> 6); }
+__device__ __forceinline__ int cell_pos(int c) { return (cell_row(c) + 1) * B_SROW + B_SCOL0 + (c & 63); }
 
-__device__ __forceinline__ void bk_push(BucketSmem& S, int sv, int c) {
-    const int idx = atomicAdd(&S.cnt[sv], 1);
-    if (idx < B_CAP) S.list[sv * B_CAP + idx] = (uint16_t)c;
-    else *(volatile uint8_t*)&S.ovf[sv] = 1;
-    if (idx == 0) atomicOr(&S.nonempty[sv >> 5], 1u << (sv & 31));
-}
-
-// g[cell] was lowered from old_bits to val: mark it open and queue it unless it already waits in the same bucket.
-__device__ __forceinline__ void bk_lowered(BucketSmem& S, int cv, float val, int old_bits, int B0, int smax) {
-    volatile uint8_t* st = S.st;
-    const uint32_t stv = st[cv];
-    st[cv] = 3;
-    const int sv = (int)val - B0;
-    if (sv <= smax && !((stv & 1u) && (int)__int_as_float(old_bits) - B0 == sv)) bk_push(S, sv, cv);
-}
-
-// Expand cell c if it is open and sits in bucket slot s (stale list entries fail one of the two tests).
-__device__ __forceinline__ void bk_expand(BucketSmem& S, int c, int s, int B0, int smax, int rh, int rw) {
-    volatile uint8_t* st = S.st;
-    if (!(st[c] & 1u)) return;
-    const int ly = c >> 6, lx = c & 63;
+// Cell c is due: pull it; if its value belongs to bucket <= b settle it and tell the out-neighbours it improves when they
+// are due; otherwise put it back with the bucket it belongs to.  The caller cleared due[c] BEFORE (clear, fence, read).
+// All shared loads are issued up front (one round trip); the 8 neighbour positions serve both as sources of the pull and as
+// targets of the notifications (target d is the source of in-edge d ^ 4).
+__device__ __forceinline__ void bk_pull(BucketSmem& S, int c, int b, int B0, int smax, int rh, int rw, uint32_t& rej) {
+    const int ly = cell_row(c), lx = c & 63;
     const int pos = (ly + 1) * B_SROW + B_SCOL0 + lx;
-    const float gu = *(volatile float*)&S.g[pos];
-    if ((int)gu - B0 != s) return;
-    st[c] = 2;
-    const uint32_t m = S.om[c];
+    float ng[8];          // g of the neighbour at pos + OFF[d]
+    uint32_t nm[8];       // its in-edge mask
+    uint32_t nd[8];       // its due byte (own cells only)
+    int ncell[8];
+    uint32_t mine = 0;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-        if (!((m >> d) & 1u)) continue;
-        const float w = (d != 0 && ((m >> (8 + d)) & 1u)) ? kSqrt2F : 1.0f;
-        const float cand = gu + w;
         const int di = nb_di(d), dj = nb_dj(d);
-        const int pv = pos + di * B_SROW + dj;
-        const int cb = __float_as_int(cand);
-        const int old = atomicMin(reinterpret_cast<int*>(S.g) + pv, cb);
-        if (old > cb) {
-            if ((unsigned)(ly + di) < (unsigned)rh && (unsigned)(lx + dj) < (unsigned)rw) bk_lowered(S, c + di * BT + dj, cand, old, B0, smax);
-            else atomicOr(&S.hdirty[pv >> 5], 1u << (pv & 31));
+        const int wp = pos + di * B_SROW + dj;
+        ng[d] = S.g[wp];
+        nm[d] = S.im[wp];
+        const bool in = (unsigned)(ly + di) < (unsigned)rh && (unsigned)(lx + dj) < (unsigned)rw;
+        mine |= (uint32_t)in << d;
+        ncell[d] = in ? cell_of(ly + di, lx + dj) : c;
+        nd[d] = S.due[ncell[d]];
+    }
+    const uint32_t m = S.im[pos];
+    const float gv = S.g[pos];
+    const uint32_t stv = S.st[c];
+    float cd[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        // in-edge d arrives from u = v - OFF[d] = v + OFF[d ^ 4]
+        const float w = ((m >> d) & 1u) ? (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f) : __uint_as_float(kNoKey);
+        cd[d] = ng[d ^ 4] + w;
+    }
+    const float best = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
+    const float nv = fminf(gv, best);
+    if (!(nv < gv) && !(stv & 1u)) return;                                // a stale due byte: settled and expanded already
+    const int bk = (int)nv - B0;
+    if (bk > b) {                                                         // not yet: its bucket comes later
+        if (bk <= smax) S.due[c] = (uint8_t)(1 + bk);
+        else if (nv < gv) { S.g[pos] = nv; S.st[c] = 3; }                 // beyond the band: keep the value, the cell stays open
+        return;
+    }
+    S.g[pos] = nv;
+    asm volatile("" ::: "memory");                                        // the value before the due bytes that announce it
+    bool keep_open = false;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        if (!((nm[d] >> d) & 1u)) continue;                               // no edge v -> w (w blocked, row guard, shard window)
+        const float cnd = nv + ((d != 0 && ((nm[d] >> (8 + d)) & 1u)) ? kSqrt2F : 1.0f);
+        if (!(ng[d] > cnd)) continue;
+        if ((mine >> d) & 1u) {
+            const int bw = max((int)cnd - B0, 0);
+            if (bw <= smax) {
+                // nd[d] was read BEFORE my value was stored, so w's owner may have consumed it meanwhile without seeing my value:
+                // always store (the smaller of the two: too early only costs a look, too late would settle w out of order)
+                S.due[ncell[d]] = (uint8_t)((nd[d] != 0u && nd[d] < (uint32_t)(1 + bw)) ? nd[d] : (uint32_t)(1 + bw));
+            } else {
+                keep_open = true;                                         // beyond the band: this cell is expanded again next visit,
+                rej = min(rej, __float_as_uint(cnd));                     // which the tile asks for at the value it could not place
+            }
+        } else {
+            const int wp = pos + nb_di(d) * B_SROW + nb_dj(d);
+            const int cb = __float_as_int(cnd);
+            const int old = atomicMin(reinterpret_cast<int*>(S.g) + wp, cb);
+            if (old > cb) atomicOr(&S.hdirty[wp >> 5], 1u << (wp & 31));
         }
     }
+    S.st[c] = keep_open ? 3 : 2;
 }
 
 // ---- the courier warp's two jobs ---------------------------------------------------------------------------------
@@ -196,7 +231,7 @@ __device__ __forceinline__ int courier_read_border(const FieldParams& p, BucketS
             else if (i < 2 * rw) { ly = rh - 1; lx = i - rw; }
             else if (i < 2 * rw + rh) { ly = i - 2 * rw; lx = 0; }
             else { ly = i - 2 * rw - rh; lx = rw - 1; }
-            cells[q] = ly * BT + lx;
+            cells[q] = cell_of(ly, lx);
             vals[q] = __float_as_uint(__ldcg(p.g + (long long)(r0 + ly) * p.W + (c0 + lx)));
         }
     }
@@ -217,7 +252,7 @@ __device__ __forceinline__ int courier_read_border(const FieldParams& p, BucketS
 
 __device__ __forceinline__ void courier_loop(const FieldParams& p, BucketSmem& S, int tile, int ty, int tx, int r0, int c0, int rh, int rw,
                                              int B0, int smax, int lane) {
-    const float lo_f = (float)B0, hi_f = (float)(B0 + smax + 1);
+    const float hi_f = (float)(B0 + smax + 1);
     for (int it = 0; it < (1 << 24); ++it) {
         const int we = *(volatile int*)&S.want_end;
         const int cf = *(volatile int*)&S.ctl;
@@ -229,11 +264,7 @@ __device__ __forceinline__ void courier_loop(const FieldParams& p, BucketSmem& S
         bool took = false;
         if (pk != kNoKey && pk <= p.cap) {
             const float pkf = __uint_as_float(pk);
-            if (pkf < lo_f) {                                             // below this visit's buckets: end it, the tile is re-claimed
-                if (lane == 0) atomicOr(&S.ctl, kStop);
-                return;
-            }
-            if (pkf < hi_f) {
+            if (pkf < hi_f) {                                             // within the band (values below B0 are simply overdue)
                 if (lane == 0) {
                     atomicExch(p.tile_key + tile, kNoKey);
                     __threadfence();
@@ -264,123 +295,179 @@ __device__ __forceinline__ void courier_loop(const FieldParams& p, BucketSmem& S
 }
 
 // ---- the workers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void worker_loop(const FieldParams& p, BucketSmem& S, int B0, int smax, int rh, int rw, int tid) {
-    int s_prev = -1, it = 0, steps = 0;
+__device__ __forceinline__ void worker_loop(const FieldParams& p, BucketSmem& S, int B0, int smax, int rh, int rw, int tid, uint32_t& rej) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int b = -1;                   // nothing is due at -1: the first round only finds the smallest bucket and jumps there
+    int it = 0, steps = 0;
+    long long pa = 0, pb = 0, pc = 0, npull = 0;
     for (;;) {
+        const long long q0 = clock64();
+        // ---- my 16 due bytes: which cells are due now, and the earliest bucket anything of mine is due in ----
+        const uint4 f4 = reinterpret_cast<const uint4*>(S.due)[tid];      // re-read every round (the barrier is a memory clobber)
+        uint32_t duebits = 0;
+        int mymin = 255;
+        if (f4.x | f4.y | f4.z | f4.w) {
+            const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int e = (int)((fw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                if (e) {
+                    mymin = min(mymin, e - 1);
+                    if (e - 1 <= b) duebits |= 1u << k;
+                }
+            }
+        }
+        const int ndue = __popc(duebits);
+        int incl = ndue;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int wmn = __reduce_min_sync(0xffffffffu, mymin);
+        const long long q1 = clock64();
+        npull += total;
+        if (total) {
+            int at = incl - ndue;
+            while (duebits) {
+                const int k = __ffs(duebits) - 1;
+                duebits &= duebits - 1;
+                const int c = tid * 16 + k;
+                S.wl[warp][at++] = (uint16_t)c;
+                *(volatile uint8_t*)&S.due[c] = 0;                        // clear first, then (fence) read the neighbours
+            }
+            __threadfence_block();
+            __syncwarp();
+            for (int e = lane; e < total; e += 32) bk_pull(S, S.wl[warp][e], b, B0, smax, rh, rw, rej);
+        }
+        if (lane == 0) { *(volatile int*)&S.wcnt[it & 1][warp] = total; *(volatile int*)&S.wmin[it & 1][warp] = wmn; }
         if (tid == 0) *(volatile int*)&S.dec[it & 1] = *(volatile int*)&S.ctl;
+        const long long q2 = clock64();
         bar_workers();
         int f = *(volatile int*)&S.dec[it & 1];
+        int tot = 0, mn = 255;
+        {
+            const int4 c0 = *reinterpret_cast<const int4*>(&S.wcnt[it & 1][0]), c1 = *reinterpret_cast<const int4*>(&S.wcnt[it & 1][4]);
+            const int4 m0 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][0]), m1 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][4]);
+            tot = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+            mn = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
+        }
         ++it;
-        if (tid == 0 && s_prev >= 0) {                                    // the bucket of the last step is spent
-            *(volatile int*)&S.cnt[s_prev] = 0;
-            *(volatile uint8_t*)&S.ovf[s_prev] = 0;
-            atomicAnd(&S.nonempty[s_prev >> 5], ~(1u << (s_prev & 31)));
-        }
+        { const long long q3 = clock64(); pa += q1 - q0; pb += q2 - q1; pc += q3 - q2; }
         if (f & kStop) break;
-        int s = -1;
+        int b_next = tot ? b + 1 : (mn <= smax ? mn : 255);               // nothing was due: jump to the next bucket that holds something
+        if (tot) ++steps;
         if (!(f & kIn)) {
-            const uint4 ne = *reinterpret_cast<const uint4*>(S.nonempty);   // after the barrier (memory clobber): re-read every step
-            const int a = s_prev + 1;                                     // slots <= s_prev are spent (their bits may still read 1)
-            auto from = [](uint32_t w, int a0) { return a0 >= 32 ? 0u : (a0 > 0 ? w & (0xffffffffu << a0) : w); };
-            const uint32_t w0 = from(ne.x, a), w1 = from(ne.y, a - 32), w2 = from(ne.z, a - 64), w3 = from(ne.w, a - 96);
-            s = w0 ? __ffs(w0) - 1 : (w1 ? 31 + __ffs(w1) : (w2 ? 63 + __ffs(w2) : (w3 ? 95 + __ffs(w3) : -1)));
-            if (s < 0) {
-                // out of work: ask the courier whether anything arrived for this tile meanwhile
-                if (tid == 0) {
-                    atomicExch(&S.want_end, 1);
-                    int ff = 0, spins = 0;
-                    while (!(ff = *(volatile int*)&S.ctl)) {
-                        __nanosleep(40);
-                        if (++spins > (1 << 24)) { atomicOr(p.counts + 4, 2); atomicOr(&S.ctl, kStop); }
-                    }
-                    *(volatile int*)&S.dec[2] = ff;
+            if (b_next <= smax) { b = b_next; continue; }
+            // out of work: ask the courier whether anything arrived for this tile meanwhile
+            if (tid == 0) {
+                atomicExch(&S.want_end, 1);
+                int ff = 0, spins = 0;
+                const long long t_w = clock64();
+                while (!(ff = *(volatile int*)&S.ctl)) {
+                    __nanosleep(40);
+                    if (++spins > (1 << 24)) { atomicOr(p.counts + 4, 2); atomicOr(&S.ctl, kStop); }
                 }
-                bar_workers();
-                f = *(volatile int*)&S.dec[2];
-                if (!(f & kIn)) break;                                    // kEnd or kStop
-            }
-        }
-        if (f & kIn) {
-            // lower border values from the courier: merge them, queue the cells, start again from the lowest bucket
-            bar_workers();                                                // thread 0's reset of s_prev is done
-            const int n = *(volatile int*)&S.in_cnt;
-            for (int e = tid; e < n; e += B_WORKERS) {
-                const int c = S.inbox_cell[e];
-                const uint32_t vb = S.inbox_val[e];
-                const int old = atomicMin(reinterpret_cast<int*>(S.g) + cell_pos(c), (int)vb);
-                if (old > (int)vb) {
-                    const float val = __uint_as_float(vb);
-                    if ((int)val - B0 < 0) { *(volatile uint8_t*)&S.st[c] = 3; atomicOr(&S.ctl, kStop); }
-                    else bk_lowered(S, c, val, old, B0, smax);
-                }
+                *(volatile int*)&S.dec[2] = ff;
+                atomicAdd(p.counts + 15, (int)((clock64() - t_w) >> 4));
             }
             bar_workers();
-            if (tid == 0) {
-                *(volatile int*)&S.in_cnt = 0;
-                *(volatile int*)&S.want_end = 0;
-                __threadfence_block();
-                atomicAnd(&S.ctl, ~kIn);
+            f = *(volatile int*)&S.dec[2];
+            if (!(f & kIn)) break;                                        // kEnd or kStop
+        }
+        // lower border values from the courier: take them over, the cells are open and due in their own buckets
+        const int n = *(volatile int*)&S.in_cnt;
+        int amin = 255;
+        for (int e = tid; e < n; e += B_WORKERS) {
+            const int c = S.inbox_cell[e];
+            const uint32_t vb = S.inbox_val[e];
+            const int pos = cell_pos(c);
+            if (vb < __float_as_uint(S.g[pos])) {
+                S.g[pos] = __uint_as_float(vb);
+                S.st[c] = 3;
+                const int bk = max((int)__uint_as_float(vb) - B0, 0);
+                if (bk <= smax) { S.due[c] = (uint8_t)(1 + bk); amin = min(amin, bk); }
             }
-            s_prev = -1;
-            continue;
         }
-        const int n = *(volatile int*)&S.cnt[s];
-        if (!*(volatile uint8_t*)&S.ovf[s]) {
-            if (tid < n) bk_expand(S, S.list[s * B_CAP + tid], s, B0, smax, rh, rw);
-        } else {
-            for (int c = tid; c < BT * BT; c += B_WORKERS) bk_expand(S, c, s, B0, smax, rh, rw);
+        amin = __reduce_min_sync(0xffffffffu, amin);
+        if (lane == 0) *(volatile int*)&S.wmin[it & 1][warp] = amin;      // the next round writes this slot only after the barrier below
+        bar_workers();
+        {
+            const int4 m0 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][0]), m1 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][4]);
+            amin = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
         }
-        s_prev = s;
-        ++steps;
+        if (tid == 0) {
+            *(volatile int*)&S.in_cnt = 0;
+            *(volatile int*)&S.want_end = 0;
+            __threadfence_block();
+            atomicAnd(&S.ctl, ~kIn);
+        }
+        b = min(b_next, amin);
+        bar_workers();                                                    // everybody has read the minima before the next round overwrites them
     }
-    if (tid == 0) atomicAdd(p.counts + 8, steps);
+    if (tid == 0) { atomicAdd(p.counts + 8, steps); atomicAdd(p.counts + 14, it); }
+    if (lane == 0 && p.prof) {
+        atomicAdd(p.prof + 0 + warp * 4, (unsigned long long)pa); atomicAdd(p.prof + 1 + warp * 4, (unsigned long long)pb);
+        atomicAdd(p.prof + 2 + warp * 4, (unsigned long long)pc); atomicAdd(p.prof + 3 + warp * 4, (unsigned long long)npull);
+    }
 }
 
-// One visit of one tile: stage, expand bucket by bucket, write back.
-__device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile, uint32_t key0) {
+// One visit of one tile: stage, settle bucket by bucket, write back.
+__device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     const int r0 = ty * BT, c0 = tx * BT;
     const int W = p.W;
     const long long N = p.N;
     const int rh = min(BT, p.H - r0), rw = min(BT, W - c0);
-    const bool win = p.win_lo > 0 || p.win_hi < N;
 
-    if (tid < B_NB) { S.cnt[tid] = 0; S.ovf[tid] = 0; }
+    const long long t_a = clock64();
     for (int i = tid; i < B_HDW + 3; i += B_THREADS) S.hdirty[i] = 0;
-    if (tid < 4) S.nonempty[tid] = 0;
     if (tid < 16) S.post_min[tid] = kNoKey;
     if (tid == 0) { S.ctl = 0; S.want_end = 0; S.in_cnt = 0; S.out_cnt = 0; S.red_min = kNoKey; }
     __syncthreads();
 
-    // ---- stage: position (rr, cc) holds g[(r0-1+rr)*W + (c0-1+cc)] (flat key); my cells also get mask and state ----
+    // ---- stage: position (rr, cc) holds g and in_mask of flat key (r0-1+rr)*W + (c0-1+cc); my cells also get their state ----
     uint32_t mn = kNoKey;
-    for (int idx = tid; idx < B_SROWS * (BT + 2); idx += B_THREADS) {
-        const int rr = idx / (BT + 2), cc = idx - rr * (BT + 2);
-        const int ly = rr - 1, lx = cc - 1;
-        const long long key = (long long)(r0 + ly) * W + (c0 + lx);
-        const bool in_sq = (unsigned)ly < (unsigned)BT && (unsigned)lx < (unsigned)BT;
-        const bool mine = ly >= 0 && ly < rh && lx >= 0 && lx < rw;
-        float gv = kInfF;
-        if (key >= 0 && key < N) gv = __ldcg(p.g + key);                  // L2: other SMs write g
-        S.g[rr * B_SROW + (B_SCOL0 - 1) + cc] = gv;
-        if (mine) {
-            const float gxv = __ldcg(p.gx + key);
-            uint32_t om = __ldg(p.out_mask + key);
-            if (win) {                                                    // shards: a target outside the window takes no in-edge
+    constexpr int NPOS = B_SROWS * (BT + 2);
+    for (int base = 0; base < NPOS; base += 8 * B_THREADS) {
+        // eight positions per thread with all their loads in flight together (one L2 round trip per batch, not per position)
+        float gvv[8], gxv[8];
+        uint32_t imv[8];
 #pragma unroll
-                for (int d = 0; d < 8; ++d) {
-                    const long long kv = key + nb_off(d, W);
-                    if (kv < p.win_lo || kv >= p.win_hi) om &= ~(1u << d);
-                }
+        for (int k = 0; k < 8; ++k) {
+            const int idx = base + k * B_THREADS + tid;
+            const int rr = idx / (BT + 2), cc = idx - rr * (BT + 2);
+            const int ly = rr - 1, lx = cc - 1;
+            const long long key = (long long)(r0 + ly) * W + (c0 + lx);
+            gvv[k] = kInfF; gxv[k] = 0.f; imv[k] = 0;
+            if (idx < NPOS && key >= 0 && key < N) {
+                gvv[k] = __ldcg(p.g + key);                               // through L2: other SMs write g
+                imv[k] = __ldg(p.in_mask + key);
+                if (ly >= 0 && ly < rh && lx >= 0 && lx < rw) gxv[k] = __ldcg(p.gx + key);
             }
-            const bool open = gv < gxv;
-            S.om[ly * BT + lx] = (uint16_t)om;
-            S.st[ly * BT + lx] = open ? 3 : 0;
-            if (open) mn = min(mn, __float_as_uint(gv));
-        } else if (in_sq) {
-            S.om[ly * BT + lx] = 0;
-            S.st[ly * BT + lx] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int idx = base + k * B_THREADS + tid;
+            if (idx >= NPOS) continue;
+            const int rr = idx / (BT + 2), cc = idx - rr * (BT + 2);
+            const int ly = rr - 1, lx = cc - 1;
+            const bool in_sq = (unsigned)ly < (unsigned)BT && (unsigned)lx < (unsigned)BT;
+            const bool mine = ly >= 0 && ly < rh && lx >= 0 && lx < rw;
+            const int sp = rr * B_SROW + (B_SCOL0 - 1) + cc;
+            S.g[sp] = gvv[k];
+            S.im[sp] = (uint16_t)imv[k];
+            if (mine) {
+                const bool open = gvv[k] < gxv[k];
+                S.st[cell_of(ly, lx)] = open ? 3 : 0;
+                S.due[cell_of(ly, lx)] = open ? 1 : 0;                    // looked at in the first round, which files it under its bucket
+                if (open) mn = min(mn, __float_as_uint(gvv[k]));
+            } else if (in_sq) {
+                S.st[cell_of(ly, lx)] = 0;
+                S.due[cell_of(ly, lx)] = 0;
+            }
         }
     }
     mn = __reduce_min_sync(0xffffffffu, mn);
@@ -391,21 +478,19 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile, uint
     int B0 = 0, smax = -1;
     if (work) {
         B0 = (int)__uint_as_float(mn);
-        smax = min(B_NB - 1, (int)p.delta);
+        smax = min(B_MAXBAND, (int)p.delta);
         if (p.cap < kNoKey - 1u) smax = min(smax, (int)__uint_as_float(p.cap) - B0);
-        for (int c = tid; c < BT * BT; c += B_THREADS)
-            if (S.st[c] & 1u) {
-                const int sv = (int)S.g[cell_pos(c)] - B0;
-                if (sv <= smax) bk_push(S, sv, c);
-            }
     }
     __syncthreads();
     if (tid == 0) S.red_min = kNoKey;
+    uint32_t rej = kNoKey;        // the smallest value this visit could not place (beyond the band / the cap): the tile's next key
+    const long long t_b = clock64();
     if (work) {
-        if (tid < B_WORKERS) worker_loop(p, S, B0, smax, rh, rw, tid);
+        if (tid < B_WORKERS) worker_loop(p, S, B0, smax, rh, rw, tid, rej);
         else courier_loop(p, S, tile, ty, tx, r0, c0, rh, rw, B0, smax, lane);
     }
     __syncthreads();
+    const long long t_c = clock64();
 
     // ---- end of the visit: the courier flushes what is still dirty, the workers write the tile back --------------------
     if (work) {
@@ -418,23 +503,36 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile, uint
                 const int n = *(volatile int*)&S.in_cnt;
                 for (int e = tid; e < n; e += B_WORKERS) {
                     const int c = S.inbox_cell[e];
-                    const int old = atomicMin(reinterpret_cast<int*>(S.g) + cell_pos(c), (int)S.inbox_val[e]);
-                    if (old > (int)S.inbox_val[e]) *(volatile uint8_t*)&S.st[c] = 3;
+                    const int pos = cell_pos(c);
+                    if (S.inbox_val[e] < __float_as_uint(S.g[pos])) { S.g[pos] = __uint_as_float(S.inbox_val[e]); S.st[c] = 3; }
                 }
             }
             bar_workers();
-            uint32_t rej = kNoKey;
+            const bool stopped = *(volatile int*)&S.ctl & kStop;
             for (int c = tid; c < BT * BT; c += B_WORKERS) {
-                const uint32_t st = S.st[c];
-                if (!(st & 2u)) continue;
-                const int ly = c >> 6, lx = c & 63;
+                uint32_t st = S.st[c];
+                const int ly = cell_row(c), lx = c & 63;
                 const long long key = (long long)(r0 + ly) * W + (c0 + lx);
                 const float gv = S.g[cell_pos(c)];
+                // a due byte left over (the visit was stopped, or its bucket lies beyond the band): one of its in-neighbours holds a
+                // value this cell has not taken yet; take it now so the cell itself is open and the tile's key covers it
+                if (S.due[c]) {
+                    const uint32_t m = S.im[cell_pos(c)];
+                    float best = gv;
+#pragma unroll
+                    for (int d = 0; d < 8; ++d)
+                        if ((m >> d) & 1u) best = fminf(best, S.g[cell_pos(c) - nb_di(d) * B_SROW - nb_dj(d)] + (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f));
+                    if (best < gv) { S.g[cell_pos(c)] = best; st = 3; }
+                }
+                if (!(st & 2u)) continue;
+                const float gw = S.g[cell_pos(c)];
                 // border cells are lowered by the neighbours' couriers too: never raise them
-                if (ly == 0 || ly == rh - 1 || lx == 0 || lx == rw - 1) atomicMin(reinterpret_cast<uint32_t*>(p.g) + key, __float_as_uint(gv));
-                else __stcg(p.g + key, gv);
-                if (st & 1u) rej = min(rej, __float_as_uint(gv));         // still open: this tile wants another visit at that key
-                else __stcg(p.gx + key, gv);
+                if (ly == 0 || ly == rh - 1 || lx == 0 || lx == rw - 1) atomicMin(reinterpret_cast<uint32_t*>(p.g) + key, __float_as_uint(gw));
+                else __stcg(p.g + key, gw);
+                // still open: beyond the band the tile wants another visit at that value; within it (a cell some of whose out-edges
+                // reach beyond the band) the rejected candidates were collected while expanding
+                if (st & 1u) { if ((int)gw - B0 > smax || stopped) rej = min(rej, __float_as_uint(gw)); }
+                else __stcg(p.gx + key, gw);
             }
             rej = __reduce_min_sync(0xffffffffu, rej);
             if (lane == 0 && rej != kNoKey) atomicMin(&S.red_min, rej);
@@ -452,9 +550,12 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile, uint
         atomicAdd(p.gcount, net);
         atomicAdd(p.counts + 3, 1);
         if (!work) atomicAdd(p.counts + 10, 1);
+        const long long t_d = clock64();
+        atomicAdd(p.counts + 11, (int)((t_b - t_a) >> 4));    // cycles / 16: stage, bucket loop, write-back
+        atomicAdd(p.counts + 12, (int)((t_c - t_b) >> 4));
+        atomicAdd(p.counts + 13, (int)((t_d - t_c) >> 4));
     }
     __syncthreads();
-    (void)key0;
 }
 
 __global__ void __launch_bounds__(B_THREADS, 3) field_solve_bucket_kernel(FieldParams p) {
@@ -497,7 +598,7 @@ __global__ void __launch_bounds__(B_THREADS, 3) field_solve_bucket_kernel(FieldP
         const uint32_t my_key = S.key;
         __syncthreads();
         if (my_key == kNoKey) continue;
-        bucket_visit(p, S, tile, my_key);
+        bucket_visit(p, S, tile);
     }
 }
 
@@ -510,7 +611,7 @@ int launch_field_relax_bucket(nsfs_planner* h, FieldParams p) {
     p.out_mask = h->d_out_mask;
     p.win_lo = (long long)(h->opt_active_row_lo > 0 ? h->opt_active_row_lo : 0) * h->W;
     p.win_hi = h->opt_active_row_hi > 0 ? (long long)h->opt_active_row_hi * h->W : h->N;
-    p.delta = h->opt_field_delta > 0 ? (float)(h->opt_field_delta < B_NB - 1 ? h->opt_field_delta : B_NB - 1) : 100.0f;
+    p.delta = h->opt_field_delta > 0 ? (float)(h->opt_field_delta < B_MAXBAND ? h->opt_field_delta : B_MAXBAND) : 128.0f;
     const size_t smem = sizeof(BucketSmem);
     NSFS_CUDA_TRY(h, cudaFuncSetAttribute(field_solve_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
     int per_sm = 0;
@@ -520,11 +621,25 @@ int launch_field_relax_bucket(nsfs_planner* h, FieldParams p) {
     int grid = per_sm * h->sm_count;
     const int n_tiles = f.tiles_x * f.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
+    static unsigned long long* d_prof = nullptr;
+    const bool prof = getenv("NSFS_FIELD_DEBUG") != nullptr;
+    if (prof) {
+        if (!d_prof) cudaMalloc(&d_prof, 64 * 8);
+        cudaMemsetAsync(d_prof, 0, 64 * 8, h->stream);
+        p.prof = d_prof;
+    }
     void* args[] = {&p};
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
     NSFS_CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)field_solve_bucket_kernel, dim3(grid), dim3(B_THREADS), args, smem, h->stream));
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
+    if (prof) {
+        unsigned long long hp[64];
+        cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        for (int w = 0; w < 8; ++w)
+            fprintf(stderr, "[bucket prof] warp %d: scan %llu pull %llu barrier %llu cycles, %llu cells pulled\n", w, hp[4 * w], hp[4 * w + 1], hp[4 * w + 2], hp[4 * w + 3]);
+    }
     return NSFS_OK;
 }
 
