@@ -95,6 +95,13 @@ int nsfs_get_packed_map_device(nsfs_t* h, const uint32_t** d_free, const uint32_
 int nsfs_set_packed_map_device(nsfs_t* h, const uint32_t* d_free, const uint32_t* d_inflated);
 /* testPos(Index) for a batch of cells (core.cpp:434-455): out = 1 free, 0 not free / row out of range, -1 would throw */
 int nsfs_test_pos_batch(nsfs_t* h, int n, const int32_t* ij, int8_t* out);
+/* The path consumer's check of what the planner handed it.
+ * replaces: Commander::checkTrajectorySafety + checkCell + oob (commander.cpp:316-384,394-397) on the trajectory's cells
+ * (ij = Commander::pos2idx of each point, 386-391; n points, host pointer).  Same results: n == 0 -> (safe 0, bad_idx -2);
+ * n == 1 -> point 0 decides, bad_idx -1; else points t_id, t_id-1 .. 0 and the first unsafe one is bad_idx (safe 1, -1 when
+ * none).  The commander's oob treats row 0 as outside and never tests the column.  NSFS_E_RANGE where the reference
+ * throws std::out_of_range (t_id >= n, or a key outside the planes) before meeting an unsafe point. */
+int nsfs_check_trajectory(nsfs_t* h, int n, const int32_t* ij, int t_id, int* safe, int* bad_idx);
 
 /* ---- single query --------------------------------------------------------------------------------
  * replaces: GridPlannerCore::plan(Index, Index, MapData&) of the selected child.

@@ -100,6 +100,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
         rc = ensure_scratch(h, 1 << 16);
     } while (0);
     if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
+    if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
     *out = h;
     return NSFS_OK;
 }
@@ -240,6 +241,31 @@ int nsfs_test_pos_batch(nsfs_t* h, int n, const int32_t* ij, int8_t* out) {
     if ((rc = launch_test_pos(h, n, (const int32_t*)d, (int8_t*)(d + in_b))) != NSFS_OK) return rc;
     NSFS_CUDA_TRY(h, cudaMemcpyAsync(out, d + in_b, n, cudaMemcpyDeviceToHost, h->stream));
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NSFS_OK;
+}
+
+int nsfs_check_trajectory(nsfs_t* h, int n, const int32_t* ij, int t_id, int* safe, int* bad_idx) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (n < 0 || (n && !ij) || !safe || !bad_idx) return NSFS_E_ARG;
+    if (n == 0) { *safe = 0; *bad_idx = -2; return NSFS_OK; }                      // commander.cpp:320-324
+    const bool single = n == 1;                                                     // 326-340: only point 0, reported as index -1
+    const int last = single ? 0 : t_id;
+    *safe = 1; *bad_idx = -1;
+    if (last < 0) return NSFS_OK;                                                   // the loop body never runs
+    const size_t in_b = align_up((size_t)n * 8, 256);
+    if ((rc = ensure_scratch(h, in_b + 256)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    int first_bad = -1;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d, ij, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(d + in_b, &first_bad, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_trajectory_check(h, n, (const int32_t*)d, last, (int*)(d + in_b))) != NSFS_OK) return rc;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&first_bad, d + in_b, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (first_bad < 0) return NSFS_OK;
+    if (first_bad & 1) return NSFS_E_RANGE;                                         // the first point the reference would trip over throws
+    *safe = 0;
+    *bad_idx = single ? -1 : (first_bad >> 1);
     return NSFS_OK;
 }
 

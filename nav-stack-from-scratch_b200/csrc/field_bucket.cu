@@ -40,7 +40,10 @@ constexpr int B_SCOL0 = 4;                      // smem column of tile column 0 
 constexpr int B_SROWS = BT + 2;
 constexpr int B_POS = B_SROWS * B_SROW;         // staged positions (4752)
 constexpr int B_HDW = (B_POS + 31) / 32;        // words of the dirty-halo bit map
-constexpr int B_MAXBAND = 250;                  // due bytes hold 1 + (bucket - B0)
+constexpr int B_MAXBAND = 125;                  // due bytes hold 1 + (bucket - B0) <= 126 (0x7f stands for "none" in the min scan)
+#ifndef NSFS_BUCKET_FENCE
+#define NSFS_BUCKET_FENCE 0                     // 1: a CTA fence between clearing due bytes and pulling (A/B check of the ordering argument)
+#endif
 constexpr int B_WORKERS = 256;
 constexpr int B_WARPS = B_WORKERS / 32;
 constexpr int B_THREADS = B_WORKERS + 32;       // + the courier warp
@@ -51,12 +54,12 @@ static_assert(B_WORKERS * 16 == BT * BT, "one worker per 16 due bytes");
 
 struct __align__(16) BucketSmem {
     float g[B_POS];
-    uint16_t im[B_POS];
-    uint8_t due[BT * BT];    // 0 = idle, else 1 + (bucket - B0) the cell is due in
+    uint32_t mask[BT * BT];  // in-edge mask | out-edge mask << 16 (map_pack.cu), own cells only
+    uint8_t due[BT * BT];    // 0 = idle, else 1 + (bucket - B0) the cell is due in (<= 127: the scan compares 4 bytes per instruction)
     uint8_t st[BT * BT];     // bit 0: open (lowered / re-opened, not expanded at its value); bit 1: touched in this visit (write back)
     uint16_t wl[B_WARPS][512];
-    int wcnt[2][B_WARPS];
-    int wmin[2][B_WARPS];
+    uint16_t wcnt[2][B_WARPS];
+    int wmin[B_WARPS];
     uint32_t hdirty[B_HDW + 3];
     uint32_t inbox_val[256];
     uint32_t post_min[16];
@@ -75,44 +78,41 @@ struct __align__(16) BucketSmem {
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(B_WORKERS) : "memory"); }
 
-// Cell ids interleave the rows over the warps (warp w owns the due bytes of cells 512w .. 512w+511 = tile rows w, w+8, w+16, ...),
-// so a wavefront crossing the tile spreads its cells over all eight work lists.  Row <-> id row: swap the two 3-bit halves.
-__device__ __forceinline__ int row_swap(int r) { return ((r & 7) << 3) | (r >> 3); }
-__device__ __forceinline__ int cell_of(int ly, int lx) { return (row_swap(ly) << 6) | lx; }
-__device__ __forceinline__ int cell_row(int c) { return row_swap(c >> 6); }
-__device__ __forceinline__ int cell_pos(int c) { return (cell_row(c) + 1) * B_SROW + B_SCOL0 + (c & 63); }
+__device__ __forceinline__ int cell_of(int ly, int lx) { return ly * BT + lx; }
+__device__ __forceinline__ int cell_row(int c) { return c >> 6; }
+__device__ __forceinline__ int cell_pos(int c) { return c + ((c >> 6) << 3) + (B_SROW + B_SCOL0); }   // (ly + 1) * 72 + 4 + lx
 
 // Cell c is due: pull it; if its value belongs to bucket <= b settle it and tell the out-neighbours it improves when they
-// are due; otherwise put it back with the bucket it belongs to.  The caller cleared due[c] BEFORE (clear, fence, read).
+// are due; otherwise put it back with the bucket it belongs to.  The caller cleared due[c] BEFORE (clear, then read).
 // All shared loads are issued up front (one round trip); the 8 neighbour positions serve both as sources of the pull and as
-// targets of the notifications (target d is the source of in-edge d ^ 4).
+// targets of the notifications (target d is the source of in-edge d ^ 4).  INTERIOR: all 8 neighbours are cells of this tile.
+template <bool INTERIOR>
 __device__ __forceinline__ void bk_pull(BucketSmem& S, int c, int b, int B0, int smax, int rh, int rw, uint32_t& rej) {
-    const int ly = cell_row(c), lx = c & 63;
-    const int pos = (ly + 1) * B_SROW + B_SCOL0 + lx;
+    const int pos = cell_pos(c);
+    const float* gp = S.g + pos;
+    const uint8_t* dp = S.due + c;
     float ng[8];          // g of the neighbour at pos + OFF[d]
-    uint32_t nm[8];       // its in-edge mask
     uint32_t nd[8];       // its due byte (own cells only)
-    int ncell[8];
-    uint32_t mine = 0;
+    uint32_t mine = 0xffu;
+    if (!INTERIOR) {
+        const int ly = c >> 6, lx = c & 63;
+        mine = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) mine |= (uint32_t)((unsigned)(ly + nb_di(d)) < (unsigned)rh && (unsigned)(lx + nb_dj(d)) < (unsigned)rw) << d;
+    }
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-        const int di = nb_di(d), dj = nb_dj(d);
-        const int wp = pos + di * B_SROW + dj;
-        ng[d] = S.g[wp];
-        nm[d] = S.im[wp];
-        const bool in = (unsigned)(ly + di) < (unsigned)rh && (unsigned)(lx + dj) < (unsigned)rw;
-        mine |= (uint32_t)in << d;
-        ncell[d] = in ? cell_of(ly + di, lx + dj) : c;
-        nd[d] = S.due[ncell[d]];
+        ng[d] = gp[nb_di(d) * B_SROW + nb_dj(d)];
+        nd[d] = (INTERIOR || ((mine >> d) & 1u)) ? dp[nb_di(d) * BT + nb_dj(d)] : 0u;
     }
-    const uint32_t m = S.im[pos];
-    const float gv = S.g[pos];
+    const uint32_t mm = S.mask[c];
+    const float gv = gp[0];
     const uint32_t stv = S.st[c];
     float cd[8];
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
         // in-edge d arrives from u = v - OFF[d] = v + OFF[d ^ 4]
-        const float w = ((m >> d) & 1u) ? (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f) : __uint_as_float(kNoKey);
+        const float w = ((mm >> d) & 1u) ? (((mm >> (8 + d)) & 1u) ? kSqrt2F : 1.0f) : __uint_as_float(kNoKey);
         cd[d] = ng[d ^ 4] + w;
     }
     const float best = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
@@ -126,18 +126,19 @@ __device__ __forceinline__ void bk_pull(BucketSmem& S, int c, int b, int B0, int
     }
     S.g[pos] = nv;
     asm volatile("" ::: "memory");                                        // the value before the due bytes that announce it
+    const uint32_t om = mm >> 16;
     bool keep_open = false;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-        if (!((nm[d] >> d) & 1u)) continue;                               // no edge v -> w (w blocked, row guard, shard window)
-        const float cnd = nv + ((d != 0 && ((nm[d] >> (8 + d)) & 1u)) ? kSqrt2F : 1.0f);
+        if (!((om >> d) & 1u)) continue;                                  // no edge v -> w (w blocked, row guard, shard window)
+        const float cnd = nv + ((d != 0 && ((om >> (8 + d)) & 1u)) ? kSqrt2F : 1.0f);
         if (!(ng[d] > cnd)) continue;
-        if ((mine >> d) & 1u) {
-            const int bw = max((int)cnd - B0, 0);
-            if (bw <= smax) {
+        if (INTERIOR || ((mine >> d) & 1u)) {
+            const uint32_t e = (uint32_t)(1 + max((int)cnd - B0, 0));
+            if (e <= (uint32_t)(1 + smax)) {
                 // nd[d] was read BEFORE my value was stored, so w's owner may have consumed it meanwhile without seeing my value:
                 // always store (the smaller of the two: too early only costs a look, too late would settle w out of order)
-                S.due[ncell[d]] = (uint8_t)((nd[d] != 0u && nd[d] < (uint32_t)(1 + bw)) ? nd[d] : (uint32_t)(1 + bw));
+                S.due[c + nb_di(d) * BT + nb_dj(d)] = (uint8_t)((nd[d] != 0u && nd[d] < e) ? nd[d] : e);
             } else {
                 keep_open = true;                                         // beyond the band: this cell is expanded again next visit,
                 rej = min(rej, __float_as_uint(cnd));                     // which the tile asks for at the value it could not place
@@ -295,69 +296,91 @@ __device__ __forceinline__ void courier_loop(const FieldParams& p, BucketSmem& S
 }
 
 // ---- the workers ---------------------------------------------------------------------------------------------------
+// SWAR over the 4 due bytes of a word (all <= 127): bit 7 of a byte is set iff it is non-zero and <= the limit byte.
+__device__ __forceinline__ uint32_t due_le(uint32_t w, uint32_t lim4) {
+    return ((lim4 | 0x80808080u) - w) & (w + 0x7f7f7f7fu) & 0x80808080u;
+}
+
 __device__ __forceinline__ void worker_loop(const FieldParams& p, BucketSmem& S, int B0, int smax, int rh, int rw, int tid, uint32_t& rej) {
     const int lane = tid & 31, warp = tid >> 5;
-    int b = -1;                   // nothing is due at -1: the first round only finds the smallest bucket and jumps there
+    int b = 0;                    // staged open cells carry due byte 1: the first round files every one of them under its bucket
     int it = 0, steps = 0;
     long long pa = 0, pb = 0, pc = 0, npull = 0;
     for (;;) {
-        const long long q0 = clock64();
-        // ---- my 16 due bytes: which cells are due now, and the earliest bucket anything of mine is due in ----
+        const long long q0 = p.prof ? clock64() : 0;
+        // ---- my 16 due bytes: which cells are due now ----
         const uint4 f4 = reinterpret_cast<const uint4*>(S.due)[tid];      // re-read every round (the barrier is a memory clobber)
-        uint32_t duebits = 0;
-        int mymin = 255;
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
         if (f4.x | f4.y | f4.z | f4.w) {
-            const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
+            const uint32_t lim4 = (uint32_t)min(b + 1, 127) * 0x01010101u;
+            m0 = due_le(f4.x, lim4); m1 = due_le(f4.y, lim4); m2 = due_le(f4.z, lim4); m3 = due_le(f4.w, lim4);
+        }
+        const int ndue = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        int total = 0;
+        if (__any_sync(0xffffffffu, ndue)) {
+            int incl = ndue;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int e = (int)((fw[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                if (e) {
-                    mymin = min(mymin, e - 1);
-                    if (e - 1 <= b) duebits |= 1u << k;
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-        }
-        const int ndue = __popc(duebits);
-        int incl = ndue;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int wmn = __reduce_min_sync(0xffffffffu, mymin);
-        const long long q1 = clock64();
-        npull += total;
-        if (total) {
+            total = __shfl_sync(0xffffffffu, incl, 31);
             int at = incl - ndue;
-            while (duebits) {
-                const int k = __ffs(duebits) - 1;
-                duebits &= duebits - 1;
-                const int c = tid * 16 + k;
-                S.wl[warp][at++] = (uint16_t)c;
-                *(volatile uint8_t*)&S.due[c] = 0;                        // clear first, then (fence) read the neighbours
+            uint32_t mw[4] = {m0, m1, m2, m3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t m = mw[q];
+                while (m) {
+                    const int bit = __ffs(m) - 1;                         // 7, 15, 23, 31
+                    m &= m - 1;
+                    const int c = tid * 16 + q * 4 + (bit >> 3);
+                    S.wl[warp][at++] = (uint16_t)c;
+                    S.due[c] = 0;                                         // clear first, then read the neighbours (shared memory
+                }                                                         // executes one warp's accesses in order)
             }
-            __threadfence_block();
+            if (NSFS_BUCKET_FENCE || p.early == 2) __threadfence_block();  // (field_early 2: A/B check of the ordering argument)
             __syncwarp();
-            for (int e = lane; e < total; e += 32) bk_pull(S, S.wl[warp][e], b, B0, smax, rh, rw, rej);
         }
-        if (lane == 0) { *(volatile int*)&S.wcnt[it & 1][warp] = total; *(volatile int*)&S.wmin[it & 1][warp] = wmn; }
+        const long long q1 = p.prof ? clock64() : 0;
+        npull += total;
+        for (int e = lane; e < total; e += 32) {
+            const int c = S.wl[warp][e];
+            const int ly = c >> 6, lx = c & 63;
+            if ((unsigned)(ly - 1) < (unsigned)(rh - 2) && (unsigned)(lx - 1) < (unsigned)(rw - 2)) bk_pull<true>(S, c, b, B0, smax, rh, rw, rej);
+            else bk_pull<false>(S, c, b, B0, smax, rh, rw, rej);
+        }
+        if (lane == 0) *(volatile uint16_t*)&S.wcnt[it & 1][warp] = (uint16_t)total;
         if (tid == 0) *(volatile int*)&S.dec[it & 1] = *(volatile int*)&S.ctl;
-        const long long q2 = clock64();
+        const long long q2 = p.prof ? clock64() : 0;
         bar_workers();
         int f = *(volatile int*)&S.dec[it & 1];
-        int tot = 0, mn = 255;
-        {
-            const int4 c0 = *reinterpret_cast<const int4*>(&S.wcnt[it & 1][0]), c1 = *reinterpret_cast<const int4*>(&S.wcnt[it & 1][4]);
-            const int4 m0 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][0]), m1 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][4]);
-            tot = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
-            mn = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
-        }
+        const uint4 cn = *reinterpret_cast<const uint4*>(&S.wcnt[it & 1][0]);
+        const bool tot = (cn.x | cn.y | cn.z | cn.w) != 0u;
         ++it;
-        { const long long q3 = clock64(); pa += q1 - q0; pb += q2 - q1; pc += q3 - q2; }
+        if (p.prof) { const long long q3 = clock64(); pa += q1 - q0; pb += q2 - q1; pc += q3 - q2; }
         if (f & kStop) break;
-        int b_next = tot ? b + 1 : (mn <= smax ? mn : 255);               // nothing was due: jump to the next bucket that holds something
+        int b_next = b + 1;
         if (tot) ++steps;
+        if (!tot || b_next > smax) {
+            // nothing was due, or the band is used up: find the next bucket that holds something (gaps, the start, the end of
+            // the visit).  Cells settled out of order (overdue corrections) may have left due bytes BELOW b: they count too.
+            const uint4 e4 = reinterpret_cast<const uint4*>(S.due)[tid];
+            uint32_t mn4 = 0x7f7f7f7fu;
+            const uint32_t ew[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t z7 = ((ew[q] + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u;   // bit 7 of the zero bytes
+                mn4 = __vminu4(mn4, ew[q] | (z7 - (z7 >> 7)));                               // zero bytes count as 0x7f
+            }
+            int mymin = (int)min(min(mn4 & 0xffu, (mn4 >> 8) & 0xffu), min((mn4 >> 16) & 0xffu, mn4 >> 24));
+            mymin = __reduce_min_sync(0xffffffffu, mymin);
+            if (lane == 0) *(volatile int*)&S.wmin[warp] = mymin;
+            bar_workers();
+            const int4 w0 = *reinterpret_cast<const int4*>(&S.wmin[0]), w1 = *reinterpret_cast<const int4*>(&S.wmin[4]);
+            const int mn = min(min(min(w0.x, w0.y), min(w0.z, w0.w)), min(min(w1.x, w1.y), min(w1.z, w1.w)));
+            b_next = mn < 0x7f ? mn - 1 : 255;
+            bar_workers();                                                // wmin is free again
+        }
         if (!(f & kIn)) {
             if (b_next <= smax) { b = b_next; continue; }
             // out of work: ask the courier whether anything arrived for this tile meanwhile
@@ -391,11 +414,11 @@ __device__ __forceinline__ void worker_loop(const FieldParams& p, BucketSmem& S,
             }
         }
         amin = __reduce_min_sync(0xffffffffu, amin);
-        if (lane == 0) *(volatile int*)&S.wmin[it & 1][warp] = amin;      // the next round writes this slot only after the barrier below
+        if (lane == 0) *(volatile int*)&S.wmin[warp] = amin;
         bar_workers();
         {
-            const int4 m0 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][0]), m1 = *reinterpret_cast<const int4*>(&S.wmin[it & 1][4]);
-            amin = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
+            const int4 w0 = *reinterpret_cast<const int4*>(&S.wmin[0]), w1 = *reinterpret_cast<const int4*>(&S.wmin[4]);
+            amin = min(min(min(w0.x, w0.y), min(w0.z, w0.w)), min(min(w1.x, w1.y), min(w1.z, w1.w)));
         }
         if (tid == 0) {
             *(volatile int*)&S.in_cnt = 0;
@@ -404,7 +427,7 @@ __device__ __forceinline__ void worker_loop(const FieldParams& p, BucketSmem& S,
             atomicAnd(&S.ctl, ~kIn);
         }
         b = min(b_next, amin);
-        bar_workers();                                                    // everybody has read the minima before the next round overwrites them
+        bar_workers();                                                    // everybody has read the minima before they are overwritten
     }
     if (tid == 0) { atomicAdd(p.counts + 8, steps); atomicAdd(p.counts + 14, it); }
     if (lane == 0 && p.prof) {
@@ -428,24 +451,35 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile) {
     if (tid == 0) { S.ctl = 0; S.want_end = 0; S.in_cnt = 0; S.out_cnt = 0; S.red_min = kNoKey; }
     __syncthreads();
 
-    // ---- stage: position (rr, cc) holds g and in_mask of flat key (r0-1+rr)*W + (c0-1+cc); my cells also get their state ----
+    // ---- stage: position (rr, cc) holds g of flat key (r0-1+rr)*W + (c0-1+cc); my cells also get their masks and state ----
+    const bool win = p.win_lo > 0 || p.win_hi < N;
     uint32_t mn = kNoKey;
     constexpr int NPOS = B_SROWS * (BT + 2);
     for (int base = 0; base < NPOS; base += 8 * B_THREADS) {
         // eight positions per thread with all their loads in flight together (one L2 round trip per batch, not per position)
         float gvv[8], gxv[8];
-        uint32_t imv[8];
+        uint32_t mkv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int idx = base + k * B_THREADS + tid;
             const int rr = idx / (BT + 2), cc = idx - rr * (BT + 2);
             const int ly = rr - 1, lx = cc - 1;
             const long long key = (long long)(r0 + ly) * W + (c0 + lx);
-            gvv[k] = kInfF; gxv[k] = 0.f; imv[k] = 0;
+            gvv[k] = kInfF; gxv[k] = 0.f; mkv[k] = 0;
             if (idx < NPOS && key >= 0 && key < N) {
                 gvv[k] = __ldcg(p.g + key);                               // through L2: other SMs write g
-                imv[k] = __ldg(p.in_mask + key);
-                if (ly >= 0 && ly < rh && lx >= 0 && lx < rw) gxv[k] = __ldcg(p.gx + key);
+                if (ly >= 0 && ly < rh && lx >= 0 && lx < rw) {
+                    gxv[k] = __ldcg(p.gx + key);
+                    uint32_t om = __ldg(p.out_mask + key);
+                    if (win) {                                            // shards: a target outside the window takes no in-edge
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) {
+                            const long long kv = key + nb_off(d, W);
+                            if (kv < p.win_lo || kv >= p.win_hi) om &= ~(1u << d);
+                        }
+                    }
+                    mkv[k] = (uint32_t)__ldg(p.in_mask + key) | (om << 16);
+                }
             }
         }
 #pragma unroll
@@ -456,17 +490,13 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile) {
             const int ly = rr - 1, lx = cc - 1;
             const bool in_sq = (unsigned)ly < (unsigned)BT && (unsigned)lx < (unsigned)BT;
             const bool mine = ly >= 0 && ly < rh && lx >= 0 && lx < rw;
-            const int sp = rr * B_SROW + (B_SCOL0 - 1) + cc;
-            S.g[sp] = gvv[k];
-            S.im[sp] = (uint16_t)imv[k];
-            if (mine) {
-                const bool open = gvv[k] < gxv[k];
+            S.g[rr * B_SROW + (B_SCOL0 - 1) + cc] = gvv[k];
+            if (in_sq) {
+                const bool open = mine && gvv[k] < gxv[k];
+                S.mask[cell_of(ly, lx)] = mkv[k];
                 S.st[cell_of(ly, lx)] = open ? 3 : 0;
                 S.due[cell_of(ly, lx)] = open ? 1 : 0;                    // looked at in the first round, which files it under its bucket
                 if (open) mn = min(mn, __float_as_uint(gvv[k]));
-            } else if (in_sq) {
-                S.st[cell_of(ly, lx)] = 0;
-                S.due[cell_of(ly, lx)] = 0;
             }
         }
     }
@@ -516,13 +546,15 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile) {
                 const float gv = S.g[cell_pos(c)];
                 // a due byte left over (the visit was stopped, or its bucket lies beyond the band): one of its in-neighbours holds a
                 // value this cell has not taken yet; take it now so the cell itself is open and the tile's key covers it
-                if (S.due[c]) {
-                    const uint32_t m = S.im[cell_pos(c)];
+                const bool left = S.due[c] != 0;
+                if (left) {
+                    const uint32_t m = S.mask[c];
                     float best = gv;
 #pragma unroll
                     for (int d = 0; d < 8; ++d)
                         if ((m >> d) & 1u) best = fminf(best, S.g[cell_pos(c) - nb_di(d) * B_SROW - nb_dj(d)] + (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f));
-                    if (best < gv) { S.g[cell_pos(c)] = best; st = 3; }
+                    if (best < gv) S.g[cell_pos(c)] = best;
+                    st = 3;
                 }
                 if (!(st & 2u)) continue;
                 const float gw = S.g[cell_pos(c)];
@@ -531,7 +563,7 @@ __device__ void bucket_visit(const FieldParams& p, BucketSmem& S, int tile) {
                 else __stcg(p.g + key, gw);
                 // still open: beyond the band the tile wants another visit at that value; within it (a cell some of whose out-edges
                 // reach beyond the band) the rejected candidates were collected while expanding
-                if (st & 1u) { if ((int)gw - B0 > smax || stopped) rej = min(rej, __float_as_uint(gw)); }
+                if (st & 1u) { if ((int)gw - B0 > smax || stopped || left) rej = min(rej, __float_as_uint(gw)); }
                 else __stcg(p.gx + key, gw);
             }
             rej = __reduce_min_sync(0xffffffffu, rej);

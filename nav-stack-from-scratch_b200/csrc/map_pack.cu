@@ -111,6 +111,41 @@ __global__ void test_pos_kernel(const uint32_t* __restrict__ free_bits, int H, i
     out[t] = r;
 }
 
+// ---- the path consumer's safety check (reference commander.cpp:316-402) -------------------------
+// Commander::checkCell per trajectory cell with the commander's OWN oob (row 0 counts as outside, the column is never
+// tested, so the key i*W + j may alias or leave the planes, where vector::at throws), and the scan order of
+// checkTrajectorySafety: points t_id, t_id-1, ..., 0; the first one that is not safe decides.  One lane per point,
+// warps agree with __ballot_sync, blocks with one atomicMax on (index << 1 | throws): the largest index wins.
+__global__ void __launch_bounds__(256) trajectory_check_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N, int n,
+                                                               const int32_t* __restrict__ ij, int t_id, int* __restrict__ first_bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = 1;                                           // 1 safe, 0 not safe, -1 throws
+    if (t <= t_id) {
+        if (t >= n) cls = -1;                              // trajectory_.at(t) past the end
+        else {
+            const int i = ij[2 * t], j = ij[2 * t + 1];
+            const long long key = (long long)i * W + j;
+            if (i <= 0 || i >= H) cls = 0;
+            else if (key < 0 || key >= N) cls = -1;
+            else cls = bit_at(free_bits, key) ? 1 : 0;
+        }
+    }
+    const uint32_t bad = __ballot_sync(0xffffffffu, cls != 1);
+    if (bad) {
+        const int top = 31 - __clz(bad);                   // the highest index in this warp comes first in the reference's scan
+        if ((threadIdx.x & 31) == top) atomicMax(first_bad, (t << 1) | (cls < 0));
+    }
+}
+
+int launch_trajectory_check(nsfs_planner* h, int n, const int32_t* d_ij, int t_id, int* d_first_bad) {
+    const int pts = t_id + 1;
+    if (pts <= 0) return NSFS_OK;
+    trajectory_check_kernel<<<(pts + 255) / 256, 256, 0, h->stream>>>(h->d_free, h->H, h->W, h->N, n, d_ij, t_id, d_first_bad);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
+}
+
 // Packs the words that hold cells [k0, k1) (whole map: 0, N).
 static int pack_range(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo, long long k0, long long k1) {
     const long long n_words = (h->N + 31) / 32;

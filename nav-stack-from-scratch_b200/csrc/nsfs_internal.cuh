@@ -179,6 +179,7 @@ int launch_pack_map(nsfs_planner* h, const int32_t* d_infl, const int32_t* d_lo)
 int launch_build_masks(nsfs_planner* h);
 int launch_update_rows(nsfs_planner* h, int row0, int nrows);
 int launch_test_pos(nsfs_planner* h, int n, const int32_t* d_ij, int8_t* d_out);
+int launch_trajectory_check(nsfs_planner* h, int n, const int32_t* d_ij, int t_id, int* d_first_bad);
 
 int field_alloc(nsfs_planner* h);
 void field_free(nsfs_planner* h);

@@ -130,6 +130,19 @@ std::vector<Pos2D> GpuPlannerBase::post_process_path(std::vector<Pos2D>& raw_pat
     return out;
 }
 
+std::pair<bool, int> GpuPlannerBase::checkTrajectorySafety(const std::vector<Pos2D>& trajectory, int t_id, MapData& map_data) {
+    uploadMap(map_data);
+    std::vector<int32_t> ij(2 * trajectory.size());
+    for (size_t t = 0; t < trajectory.size(); ++t) {              // Commander::pos2idx (commander.cpp:386-391): the same rounding as core's
+        const Index id = toIndex(trajectory[t]);
+        ij[2 * t] = id.i; ij[2 * t + 1] = id.j;
+    }
+    int safe = 0, bad = -1;
+    const int rc = nsfs_check_trajectory(handle_, (int)trajectory.size(), ij.data(), t_id, &safe, &bad);
+    if (rc != NSFS_OK) fail(rc, "nsfs_check_trajectory");
+    return {safe != 0, bad};
+}
+
 std::vector<Pos2D> GpuPlannerBase::runPlan(int algo, Index s, Index g, MapData& map_data) {
     uploadMap(map_data);
     if (s.i < 0 || s.i >= map_height_ || s.j < 0 || s.j >= map_width_)
@@ -415,6 +428,20 @@ int nsfsh_plan_request(void* p, double rx, double ry, double gx, double gy, doub
 }
 
 // Parses a rosparam-style YAML; strings are copied into 32-byte buffers.
+// Commander::checkTrajectorySafety through the session's fallback planner handle (same map).
+int nsfsh_check_trajectory(void* p, int n, const double* xy, int t_id, int* safe, int* bad_idx) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        std::vector<bot_utils::Pos2D> traj;
+        for (int t = 0; t < n; ++t) traj.emplace_back(xy[2 * t], xy[2 * t + 1]);
+        const auto r = s->fallback->checkTrajectorySafety(traj, t_id, s->map);
+        *safe = r.first ? 1 : 0;
+        *bad_idx = r.second;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+    return 0;
+}
+
 int nsfsh_load_config(const char* yaml_path, char* planner_name, char* cost_mode, char* djikstra_backend, double* gp_rate,
                       int* verbose, int* device) {
     try {

@@ -14,6 +14,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "nsfs.h"
@@ -35,6 +36,10 @@ public:
     void setDevice(int device) { device_ = device; }
     const nsfs_stats& lastStats() const { return stats_; }
     double lastGoalCost() const { return last_g_goal_; }   // nodes[goal].g of the last plan (1e5 = unreachable)
+    // The path consumer's check of a trajectory against the current map: Commander::checkTrajectorySafety
+    // (commander.cpp:316-357) with its pos2idx / checkCell / oob (361-397).  {safe, first unsafe index | -1 | -2}; throws
+    // std::out_of_range where the reference's vector::at does.
+    std::pair<bool, int> checkTrajectorySafety(const std::vector<bot_utils::Pos2D>& trajectory, int t_id, bot_utils::MapData& map_data);
 
 protected:
     GpuPlannerBase();

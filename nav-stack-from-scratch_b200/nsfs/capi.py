@@ -65,6 +65,7 @@ def lib():
         L.nsfs_get_packed_map_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.nsfs_set_packed_map_device.argtypes = [vp, vp, vp]
         L.nsfs_test_pos_batch.argtypes = [vp, i32, vp, vp]
+        L.nsfs_check_trajectory.argtypes = [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         L.nsfs_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(dbl), C.POINTER(Stats)]
         L.nsfs_plan_batch.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_plan_batch_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
@@ -187,6 +188,14 @@ class Planner:
         out = np.zeros(len(ij), np.int8)
         self._check(self.L.nsfs_test_pos_batch(self.h, len(ij), _ptr(ij), _ptr(out)))
         return out
+
+    def check_trajectory(self, ij, t_id):
+        """Commander::checkTrajectorySafety on trajectory cells: (status, safe, bad_idx); status E_RANGE where the reference throws."""
+        ij = np.ascontiguousarray(ij, np.int32).reshape(-1, 2)
+        safe, bad = C.c_int32(0), C.c_int32(-1)
+        rc = self.L.nsfs_check_trajectory(self.h, len(ij), _ptr(ij) if len(ij) else None, int(t_id), C.byref(safe), C.byref(bad))
+        self._check(rc, allow=(E_RANGE,))
+        return rc, bool(safe.value), int(bad.value)
 
     # -- searches ----------------------------------------------------------------------------------
     def plan(self, algo, mode, start, goal, cap=None, want_path=True):

@@ -19,7 +19,7 @@ HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
 
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
-           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request")
+           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory")
 
 _libs = {}
 
@@ -46,6 +46,7 @@ def lib(so_path=None):
         L.nsfsh_main_planner_kind.argtypes = [vp]
         L.nsfsh_sparsify.argtypes = [vp, i32, vp, i32]
         L.nsfsh_plan_request.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32, C.POINTER(i32), vp, vp, vp]
+        L.nsfsh_check_trajectory.argtypes = [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         _libs[path] = L
     return _libs[path]
 
@@ -148,6 +149,17 @@ class Session:
                             backup_mode=bool(info[2]), robot_ok=bool(info[3] & 1), goal_ok=bool(info[3] & 2),
                             goal=tuple(goal), backup_robot=tuple(backup))
             cap = n.value
+
+    def check_trajectory(self, xy, t_id):
+        """Commander::checkTrajectorySafety (commander.cpp:316-357) on world-metre trajectory points against the session's map."""
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        safe, bad = C.c_int(0), C.c_int(-1)
+        rc = self.L.nsfsh_check_trajectory(self.s, len(xy), xy.ctypes.data_as(C.c_void_p), int(t_id), C.byref(safe), C.byref(bad))
+        if rc == 1:
+            return dict(status="out_of_range", safe=None, bad_idx=None)
+        if rc != 0:
+            raise PlannerError(self.L.nsfsh_error(self.s).decode())
+        return dict(status="ok", safe=bool(safe.value), bad_idx=int(bad.value))
 
     def find_better_point(self, bad, as_pos=False):
         fx, fy = C.c_double(0), C.c_double(0)

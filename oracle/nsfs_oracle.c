@@ -593,3 +593,39 @@ int nso_occ_inflation(int H, int W, const int32_t* lo, int thresh, const int32_t
     return status;
 }
 
+
+/* ---- the path consumer's safety check -----------------------------------------------------------
+ * Commander::checkCell (commander.cpp:361-384): safe iff !oob && infl[k] <= 0 && lo[k] <= lo_thresh, with the commander's OWN
+ * oob (394-397): `idx.i <= 0 || idx.i >= H || (idx.j < 0 && idx.j >= W)` - row 0 counts as outside, the column is never
+ * tested, so the key i*W + j may alias another row or leave [0, N), where vector::at throws.
+ * Returns 1 safe, 0 not, NSO_E_RANGE where the reference throws. */
+int nso_cmd_check_cell(const nso_map* m, int i, int j) {
+    if (i <= 0 || i >= m->H) return 0;
+    const long long k = (long long)i * m->W + j;
+    if (k < 0 || k >= (long long)m->H * m->W) return NSO_E_RANGE;
+    if (m->infl[k] > 0) return 0;
+    if (m->lo[k] > m->lo_thresh) return 0;
+    return 1;
+}
+
+/* Commander::checkTrajectorySafety (commander.cpp:316-357) on trajectory cells ij (pos2idx of the trajectory points,
+ * commander.cpp:386-391 == nso_pos2idx).  Empty trajectory: (unsafe, -2).  One point: that point, index -1 either way.
+ * Otherwise points t_id, t_id-1, ..., 0 in that order; the first unsafe one is returned; trajectory_.at(i) throws for
+ * i >= n (and t_id < 0 checks nothing).  Returns NSO_OK or NSO_E_RANGE. */
+int nso_cmd_check_trajectory(const nso_map* m, int n, const int32_t* ij, int t_id, int* safe, int* bad_idx) {
+    if (n == 0) { *safe = 0; *bad_idx = -2; return NSO_OK; }
+    if (n == 1) {
+        const int s = nso_cmd_check_cell(m, ij[0], ij[1]);
+        if (s < 0) return s;
+        *safe = s; *bad_idx = -1;
+        return NSO_OK;
+    }
+    for (int i = t_id; i >= 0; --i) {
+        if (i >= n) return NSO_E_RANGE;                 /* trajectory_.at(i) */
+        const int s = nso_cmd_check_cell(m, ij[2 * i], ij[2 * i + 1]);
+        if (s < 0) return s;
+        if (!s) { *safe = 0; *bad_idx = i; return NSO_OK; }
+    }
+    *safe = 1; *bad_idx = -1;
+    return NSO_OK;
+}

@@ -52,6 +52,39 @@ def have_reference_occ() -> bool:
     return os.path.exists(REF_OCC_SO)
 
 
+REF_CMD_SO = os.path.join(HERE, "_ref", "libnsfs_ref_cmd.so")
+
+
+def have_reference_cmd() -> bool:
+    return os.path.exists(REF_CMD_SO)
+
+
+def cmd_check_trajectory_reference(infl, lo, xy, t_id, lo_thresh=10, cell=0.05, origin=(0.0, 0.0)):
+    """The reference's own Commander::checkTrajectorySafety (commander.cpp:316-357, compiled unmodified): (status, safe, bad_idx),
+    status E_RANGE where it throws std::out_of_range."""
+    lib = C.CDLL(REF_CMD_SO)
+    infl = np.ascontiguousarray(infl, np.int32); lo = np.ascontiguousarray(lo, np.int32)
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    H, W = infl.shape
+    lib.nsref_cmd_check_trajectory.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                               C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    safe, bad = C.c_int(0), C.c_int(-1)
+    rc = lib.nsref_cmd_check_trajectory(H, W, infl.ctypes.data, lo.ctypes.data, lo_thresh, cell, origin[0], origin[1], len(xy),
+                                        xy.ctypes.data, int(t_id), C.byref(safe), C.byref(bad))
+    if rc == 2:
+        raise ValueError("the reference derived another map size from these extents")
+    return (E_RANGE if rc == 1 else 0), bool(safe.value), int(bad.value)
+
+
+def cmd_pos2idx_reference(xy, cell=0.05, origin=(0.0, 0.0)):
+    lib = C.CDLL(REF_CMD_SO)
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    ij = np.zeros((len(xy), 2), np.int32)
+    lib.nsref_cmd_pos2idx.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.nsref_cmd_pos2idx(cell, origin[0], origin[1], len(xy), xy.ctypes.data, ij.ctypes.data)
+    return ij
+
+
 def occ_mask(inflation_radius=0.2, cell_size=0.05):
     """generateMask restated (oracle/nsfs_oracle.c nso_occ_mask): int32 [n, 2] offsets."""
     build()
@@ -255,6 +288,22 @@ class Oracle:
             return r
         r["final_xy"] = self.post_process(self.idx2pos(r["path"]))
         return r
+
+    def cmd_check_trajectory(self, ij, t_id):
+        """Commander::checkTrajectorySafety restated (nso_cmd_check_trajectory): (status, safe, bad_idx)."""
+        ij = np.ascontiguousarray(ij, np.int32).reshape(-1, 2)
+        safe, bad = C.c_int(0), C.c_int(-1)
+        rc = self.lib.nso_cmd_check_trajectory(C.byref(self.map), len(ij), ij.ctypes.data_as(C.c_void_p), int(t_id), C.byref(safe), C.byref(bad))
+        return rc, bool(safe.value), int(bad.value)
+
+    def pos2idx(self, xy):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        out = np.zeros((len(xy), 2), np.int32)
+        i, j = C.c_int(0), C.c_int(0)
+        for t in range(len(xy)):
+            self.lib.nso_pos2idx(C.byref(self.map), C.c_double(xy[t, 0]), C.c_double(xy[t, 1]), C.byref(i), C.byref(j))
+            out[t] = (i.value, j.value)
+        return out
 
     def heap_trace(self, mode, ops):
         ops = np.ascontiguousarray(ops, np.int32).reshape(-1, 4)

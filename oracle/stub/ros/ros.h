@@ -41,6 +41,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <type_traits>
 namespace nsfs_stub {
 inline std::map<std::string, double>& params() { static std::map<std::string, double> p; return p; }
 inline std::function<void()>& spin_hook() { static std::function<void()> h; return h; }
@@ -48,6 +49,8 @@ inline std::function<bool()>& keep_running() { static std::function<bool()> h; r
 }
 namespace ros {
 struct Subscriber {};
+struct ServiceServer {};
+struct Time { double t = 0; static Time now() { return Time(); } double toSec() const { return t; } };
 struct Publisher { template <class M> void publish(const M&) const {} };
 struct Rate { explicit Rate(double) {} void sleep() {} };
 inline bool ok() { return true; }
@@ -55,10 +58,15 @@ inline void spinOnce() { if (nsfs_stub::spin_hook()) nsfs_stub::spin_hook()(); }
 class NodeHandle {
 public:
     template <class T> bool param(const std::string& name, T& out, const T& def) const {
-        auto it = nsfs_stub::params().find(name);
-        if (it == nsfs_stub::params().end()) { out = def; return false; }
-        out = static_cast<T>(it->second);
-        return true;
+        if constexpr (std::is_arithmetic<T>::value) {
+            auto it = nsfs_stub::params().find(name);
+            if (it == nsfs_stub::params().end()) { out = def; return false; }
+            out = static_cast<T>(it->second);
+            return true;
+        } else {                                                      // string parameters (commander.cpp:554,583): always the default
+            out = def;
+            return false;
+        }
     }
     bool param(const std::string& name, bool def) const {          // nh_.param("trigger_nodes", true): the loop condition
         if (name == "trigger_nodes" && nsfs_stub::keep_running()) return nsfs_stub::keep_running()();
@@ -66,6 +74,9 @@ public:
     }
     template <class M, class C> Subscriber subscribe(const std::string&, int, void (C::*)(M), C*) { return Subscriber(); }
     template <class M> Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
+    // commander.cpp: const-reference callbacks, a service, string / bool parameters with literal defaults
+    template <class M, class C> Subscriber subscribe(const std::string&, int, void (C::*)(const M&), C*) { return Subscriber(); }
+    template <class Rq, class Rs, class C> ServiceServer advertiseService(const std::string&, bool (C::*)(Rq&, Rs&), C*) { return ServiceServer(); }
 };
 }
 

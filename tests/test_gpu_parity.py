@@ -221,7 +221,8 @@ def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
     want = P.field(src)
     for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_mode": 2, "field_groups": 1}, {"field_delta": 16}, {"field_delta": 100000},
                  {"field_inner": 1}, {"field_delta_in": 8}, {"field_early": 2}, {"field_merge": 2}, {"field_early": 2, "field_merge": 2},
-                 {"field_gate": 64}, {"field_delta": 32, "field_inner": 2}):
+                 {"field_gate": 64}, {"field_delta": 32, "field_inner": 2},
+                 {"field_mode": 3}, {"field_mode": 3, "field_delta": 6}, {"field_mode": 3, "field_delta": 40, "field_groups": 1}):
         for k in ("field_mode", "field_groups", "field_delta", "field_inner", "field_delta_in", "field_early", "field_merge", "field_gate"):
             P.set_option(k, opts.get(k, 0))
         got = P.field(src)
