@@ -787,6 +787,18 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
     if (!strcmp(key, "team_heap_cap")) { h->opt_team_heap_cap = value; team_free(h); return NSFS_OK; }
     if (!strcmp(key, "search_kernel")) { h->opt_search_kernel = value; return NSFS_OK; }
+    if (!strcmp(key, "graph")) {                            // 0 reference quirk graph, 1 textbook 8-connected grid: rebuild the edge masks
+        if (value != 0 && value != 1) return NSFS_E_ARG;
+        if (h->opt_graph == value) return NSFS_OK;
+        h->opt_graph = value;
+        h->field.valid = false; h->field.begun = false;
+        if (!h->have_map) return NSFS_OK;
+        cudaSetDevice(h->device);
+        int rc = launch_build_masks(h);
+        if (rc != NSFS_OK) return rc;
+        NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return NSFS_OK;
+    }
     if (!strcmp(key, "field_inner")) { h->opt_field_inner = value; return NSFS_OK; }
     if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }

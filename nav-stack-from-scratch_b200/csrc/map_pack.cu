@@ -53,13 +53,28 @@ __global__ void __launch_bounds__(256) pack_map_kernel(const int32_t* __restrict
 }
 
 // ---- kernel 2: out-edge masks ----------------------------------------------------------------------
+// textbook = 1 (opt-in "graph" option): the grid a textbook planner would search instead of the reference's
+// quirk graph: rows AND columns are bounds-checked (no flat-key wrap, nothing throws) and a direction costs sqrt(2) iff it is a
+// diagonal (odd d in NB_LUT order), whatever the neighbourhood.  Every kernel downstream reads only these masks.
 __global__ void __launch_bounds__(256) out_mask_kernel(const uint32_t* __restrict__ free_bits, int H, int W, long long N,
-                                                       uint16_t* __restrict__ out_mask, int row0) {
+                                                       uint16_t* __restrict__ out_mask, int row0, int textbook) {
     // 2-D launch: blockIdx.y = row (no 64-bit division per cell), x = columns
     const int i = row0 + (int)blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W) return;
     const long long u = (long long)i * W + j;
     uint32_t pass = 0, diag = 0, thr = 0, card = 1;
+    if (textbook) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int ni = i + nb_di(d), nj = j + nb_dj(d);
+            if (ni < 0 || ni >= H || nj < 0 || nj >= W) continue;
+            if (!bit_at(free_bits, (long long)ni * W + nj)) continue;
+            pass |= 1u << d;
+            if (d & 1) diag |= 1u << (8 + d);
+        }
+        out_mask[u] = (uint16_t)(pass | diag);
+        return;
+    }
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
         const int ni = i + nb_di(d);
@@ -169,7 +184,7 @@ static int mask_range(nsfs_planner* h, long long k0, long long k1, long long j0,
     const long long a_hi = h->opt_active_row_hi > 0 ? h->opt_active_row_hi * (long long)h->W : h->N;
     if (k1 > k0)       // whole rows (callers pass row-aligned ranges)
         out_mask_kernel<<<dim3((unsigned)((h->W + block - 1) / block), (unsigned)((k1 - k0) / h->W)), block, 0, h->stream>>>(
-            h->d_free, h->H, h->W, h->N, h->d_out_mask, (int)(k0 / h->W));
+            h->d_free, h->H, h->W, h->N, h->d_out_mask, (int)(k0 / h->W), h->opt_graph == 1 ? 1 : 0);
     if (j1 > j0) in_mask_kernel<<<(unsigned)((j1 - j0 + block - 1) / block), block, 0, h->stream>>>(h->d_free, h->d_out_mask, h->H, h->W, h->N, a_lo, a_hi, h->d_in_mask, j0, j1);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());

@@ -155,6 +155,7 @@ struct nsfs_planner {
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
     long long opt_field_inner = 0;      // 0 = default (16)
     long long opt_field_delta = 0;      // 0 = default (128)
+    long long opt_graph = 0;            // 0 = the reference's quirk graph; 1 = textbook 8-connected grid
     long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
     long long opt_field_idle_ns = 0;    // 0 = default (1000)
     long long opt_field_alpha = -1;     // percent; < 0 = default (50); bulk-synchronous variant only

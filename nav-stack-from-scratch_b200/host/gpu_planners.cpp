@@ -67,7 +67,16 @@ void GpuPlannerBase::ensureHandle(MapData& map_data) {
     }
     const int rc = nsfs_create(&handle_, map_height_, map_width_, device_);
     if (rc != NSFS_OK) { handle_ = nullptr; fail(rc, "nsfs_create"); }
+    if (textbook_graph_) nsfs_set_option(handle_, "graph", 1);
     dirty_ = true;
+}
+
+void GpuPlannerBase::setTextbookGraph(bool on) {
+    textbook_graph_ = on;
+    if (handle_) {
+        const int rc = nsfs_set_option(handle_, "graph", on ? 1 : 0);
+        if (rc != NSFS_OK) fail(rc, "nsfs_set_option(graph)");
+    }
 }
 
 void GpuPlannerBase::uploadMap(MapData& map_data) {
@@ -234,6 +243,7 @@ PlannerConfig load_planner_config(const std::string& yaml_path) {
         if (key == "planner_name") cfg.planner_name = val;
         else if (key == "cost_mode") cfg.cost_mode = val;
         else if (key == "djikstra_backend") cfg.djikstra_backend = val;
+        else if (key == "graph") cfg.graph = val;
         else if (key == "gp_rate") cfg.gp_rate = std::atof(val.c_str());
         else if (key == "verbose_planner") cfg.verbose_planner = (val == "true" || val == "True" || val == "1");
         else if (key == "gpu_device") cfg.device = std::atoi(val.c_str());
@@ -247,6 +257,7 @@ std::shared_ptr<GridPlannerCore> make_main_planner(const PlannerConfig& cfg, Map
         if (cfg.cost_mode != "g") fprintf(stderr, "[GlobalPlanner]: Djikstra requires g cost. f/fg is set. Planner is guaranteed to fail\n");
         auto p = std::make_shared<GpuDjikstra>();
         p->setDevice(cfg.device);
+        p->setTextbookGraph(cfg.graph == "textbook");
         p->setBackend(cfg.djikstra_backend == "field" ? GpuDjikstra::Backend::Field : GpuDjikstra::Backend::Exact);
         p->prepPlanner(cfg.cost_mode, map_data);
         return p;
@@ -254,12 +265,14 @@ std::shared_ptr<GridPlannerCore> make_main_planner(const PlannerConfig& cfg, Map
     if (cfg.planner_name == "thetastar") {     // the branch the reference left commented out (global_planner.cpp:116-119)
         auto p = std::make_shared<GpuThetaStar>();
         p->setDevice(cfg.device);
+        p->setTextbookGraph(cfg.graph == "textbook");
         p->prepPlanner(cfg.cost_mode, map_data);
         return p;
     }
     if (cfg.cost_mode == "g") fprintf(stderr, "[GlobalPlanner]: Astar requires f/fg cost. g cost is set. Planner is guaranteed to fail\n");
     auto p = std::make_shared<GpuAstar>();
     p->setDevice(cfg.device);
+    p->setTextbookGraph(cfg.graph == "textbook");
     p->prepPlanner(cfg.cost_mode, map_data);
     return p;
 }
@@ -428,6 +441,17 @@ int nsfsh_plan_request(void* p, double rx, double ry, double gx, double gy, doub
 }
 
 // Parses a rosparam-style YAML; strings are copied into 32-byte buffers.
+// The opt-in textbook graph for the session's main planner (the fallback keeps the reference's graph).
+int nsfsh_set_graph(void* p, int textbook) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        auto* g = dynamic_cast<nsfs_host::GpuPlannerBase*>(s->main_planner.get());
+        if (!g) return 2;
+        g->setTextbookGraph(textbook != 0);
+    } catch (const std::exception& e) { s->error = e.what(); return 2; }
+    return 0;
+}
+
 // Commander::checkTrajectorySafety through the session's fallback planner handle (same map).
 int nsfsh_check_trajectory(void* p, int n, const double* xy, int t_id, int* safe, int* bad_idx) {
     auto* s = static_cast<Session*>(p);

@@ -34,6 +34,9 @@ public:
     void setMapSync(MapSync m) { sync_ = m; }
     void notifyMapChanged() { dirty_ = true; }
     void setDevice(int device) { device_ = device; }
+    // Opt-in: search the textbook 8-connected grid (rows and columns bounds-checked, diagonal steps
+    // sqrt(2)) instead of the reference's quirk graph.  Default false = reference behaviour.
+    void setTextbookGraph(bool on);
     const nsfs_stats& lastStats() const { return stats_; }
     double lastGoalCost() const { return last_g_goal_; }   // nodes[goal].g of the last plan (1e5 = unreachable)
     // The path consumer's check of a trajectory against the current map: Commander::checkTrajectorySafety
@@ -62,6 +65,7 @@ protected:
     int device_ = 0;
     MapSync sync_ = MapSync::EveryCall;
     bool dirty_ = true;
+    bool textbook_graph_ = false;
     nsfs_stats stats_{};
     double last_g_goal_ = 0.0;
     std::vector<int32_t> path_buf_;
@@ -116,6 +120,7 @@ struct PlannerConfig {
     std::string planner_name = "astar";   // "astar" | "djikstra" | "thetastar"; anything else => astar (global_planner.cpp:121-125)
     std::string cost_mode = "fg";         // "f" | "g" | "fg"; anything else => fg (grid_planner_core.cpp:274-281)
     std::string djikstra_backend = "exact";  // "exact" | "field"
+    std::string graph = "reference";      // "reference" (quirk graph, default) | "textbook" (plain 8-connected grid; optimal with djikstra)
     double gp_rate = 25.0;
     bool verbose_planner = false;
     int device = 0;

@@ -19,7 +19,7 @@ HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
 
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
-           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory")
+           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory", "nsfsh_set_graph")
 
 _libs = {}
 
@@ -46,6 +46,7 @@ def lib(so_path=None):
         L.nsfsh_main_planner_kind.argtypes = [vp]
         L.nsfsh_sparsify.argtypes = [vp, i32, vp, i32]
         L.nsfsh_plan_request.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32, C.POINTER(i32), vp, vp, vp]
+        L.nsfsh_set_graph.argtypes = [vp, i32]
         L.nsfsh_check_trajectory.argtypes = [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         _libs[path] = L
     return _libs[path]
@@ -149,6 +150,11 @@ class Session:
                             backup_mode=bool(info[2]), robot_ok=bool(info[3] & 1), goal_ok=bool(info[3] & 2),
                             goal=tuple(goal), backup_robot=tuple(backup))
             cap = n.value
+
+    def set_graph(self, textbook):
+        """Opt-in textbook 8-connected grid for the main planner (False = the reference's own graph)."""
+        if self.L.nsfsh_set_graph(self.s, 1 if textbook else 0) != 0:
+            raise PlannerError(self.L.nsfsh_error(self.s).decode())
 
     def check_trajectory(self, xy, t_id):
         """Commander::checkTrajectorySafety (commander.cpp:316-357) on world-metre trajectory points against the session's map."""

@@ -629,3 +629,59 @@ int nso_cmd_check_trajectory(const nso_map* m, int n, const int32_t* ij, int t_i
     *safe = 1; *bad_idx = -1;
     return NSO_OK;
 }
+
+/* ---- the opt-in textbook graph ------------------------------------------------------------------
+ * NOT reference behaviour (there is none to match): the cost-to-go field a textbook Dijkstra computes on the plain
+ * 8-connected grid over the same free cells: neighbours bounds-checked in rows AND columns, cardinal steps 1, diagonal steps
+ * sqrt(2), no corner rule (like the reference, a diagonal may pass between two blocked cells).  fp64, binary heap with lazy
+ * deletion; g = 1e5 where unreached, as the reference initialises it.  Checks the CUDA field on the "graph = 1" masks. */
+typedef struct { double g; long long k; } tb_ent;
+static void tb_push(tb_ent* h, long long* n, double g, long long k) {
+    long long c = (*n)++;
+    while (c > 0) {
+        long long p = (c - 1) / 2;
+        if (h[p].g <= g) break;
+        h[c] = h[p]; c = p;
+    }
+    h[c].g = g; h[c].k = k;
+}
+static tb_ent tb_pop(tb_ent* h, long long* n) {
+    tb_ent top = h[0], last = h[--(*n)];
+    long long c = 0;
+    for (;;) {
+        long long l = 2 * c + 1;
+        if (l >= *n) break;
+        if (l + 1 < *n && h[l + 1].g < h[l].g) l++;
+        if (h[l].g >= last.g) break;
+        h[c] = h[l]; c = l;
+    }
+    if (*n > 0) h[c] = last;
+    return top;
+}
+int nso_textbook_field(const nso_map* m, int si, int sj, double* g) {
+    static const int DI[8] = {1, 1, 0, -1, -1, -1, 0, 1}, DJ[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    const int H = m->H, W = m->W;
+    const long long N = (long long)H * W;
+    if (si < 0 || si >= H || sj < 0 || sj >= W) return NSO_E_ARG;
+    tb_ent* heap = (tb_ent*)malloc(sizeof(tb_ent) * (size_t)(8 * N + 8));
+    if (!heap) return NSO_E_NOMEM;
+    long long n = 0;
+    for (long long k = 0; k < N; ++k) g[k] = 1e5;
+    g[(long long)si * W + sj] = 0.0;
+    tb_push(heap, &n, 0.0, (long long)si * W + sj);
+    while (n > 0) {
+        const tb_ent e = tb_pop(heap, &n);
+        if (e.g > g[e.k]) continue;
+        const int i = (int)(e.k / W), j = (int)(e.k % W);
+        for (int d = 0; d < 8; ++d) {
+            const int ni = i + DI[d], nj = j + DJ[d];
+            if (ni < 0 || ni >= H || nj < 0 || nj >= W) continue;
+            const long long kv = (long long)ni * W + nj;
+            if (m->infl[kv] > 0 || m->lo[kv] > m->lo_thresh) continue;
+            const double cand = e.g + ((d & 1) ? M_SQRT2 : 1.0);
+            if (cand < g[kv]) { g[kv] = cand; tb_push(heap, &n, cand, kv); }
+        }
+    }
+    free(heap);
+    return NSO_OK;
+}

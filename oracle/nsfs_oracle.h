@@ -62,6 +62,9 @@ double nso_field_min_pending(const nso_map* m, const double* g, int row_lo, int 
 
 /* Map producer (reference loco_mapping): disc mask and the inflation plane implied by a log-odds plane. */
 int nso_occ_mask(double inflation_radius, double cell_size, int32_t* ab, int cap);
+/* opt-in textbook graph (not reference behaviour): plain 8-connected Dijkstra field, fp64, 1e5 = unreached */
+int nso_textbook_field(const nso_map* m, int si, int sj, double* g);
+
 /* the path consumer's safety check (commander.cpp:316-402) */
 int nso_cmd_check_cell(const nso_map* m, int i, int j);           /* 1 safe, 0 not, NSO_E_RANGE */
 int nso_cmd_check_trajectory(const nso_map* m, int n, const int32_t* ij, int t_id, int* safe, int* bad_idx);

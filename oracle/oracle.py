@@ -289,6 +289,13 @@ class Oracle:
         r["final_xy"] = self.post_process(self.idx2pos(r["path"]))
         return r
 
+    def textbook_field(self, start):
+        """Plain 8-connected Dijkstra (cardinal 1, diagonal sqrt 2, rows and columns bounds-checked): fp64 [H, W], 1e5 = unreached."""
+        g = np.zeros(self.H * self.W, np.float64)
+        rc = self.lib.nso_textbook_field(C.byref(self.map), int(start[0]), int(start[1]), g.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return g.reshape(self.H, self.W)
+
     def cmd_check_trajectory(self, ij, t_id):
         """Commander::checkTrajectorySafety restated (nso_cmd_check_trajectory): (status, safe, bad_idx)."""
         ij = np.ascontiguousarray(ij, np.int32).reshape(-1, 2)
