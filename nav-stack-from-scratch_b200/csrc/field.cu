@@ -58,8 +58,13 @@ __global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* 
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float4 v = make_float4(kInfF, kInfF, kInfF, kInfF);
-    for (long long k = t; k < n4; k += stride) { g4[k] = v; gx4[k] = v; }     // gx: "never expanded" (field_bucket.cu)
-    for (long long k = n4 * 4 + t; k < N; k += stride) { g[k] = kInfF; gx[k] = kInfF; }
+    if (gx4) {                                                                // gx: "never expanded" (field_bucket.cu only)
+        for (long long k = t; k < n4; k += stride) { g4[k] = v; gx4[k] = v; }
+        for (long long k = n4 * 4 + t; k < N; k += stride) { g[k] = kInfF; gx[k] = kInfF; }
+    } else {
+        for (long long k = t; k < n4; k += stride) g4[k] = v;
+        for (long long k = n4 * 4 + t; k < N; k += stride) g[k] = kInfF;
+    }
     for (long long k = t; k < n_tiles; k += stride) { tile_key[k] = kNoKey; tile_busy[k] = 0; }
 }
 
@@ -849,7 +854,6 @@ int field_alloc(nsfs_planner* h) {
     f.tiles_y = (h->H + TS - 1) / TS;
     const int n_tiles = f.tiles_x * f.tiles_y;
     NSFS_CUDA_TRY(h, cudaMalloc(&f.g, (size_t)(h->N + 4) * sizeof(float)));
-    NSFS_CUDA_TRY(h, cudaMalloc(&f.gx, (size_t)(h->N + 4) * sizeof(float)));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.pred, (size_t)h->N));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.tile_key, (size_t)(n_tiles + 32) * sizeof(uint32_t)));
     NSFS_CUDA_TRY(h, cudaMalloc(&f.list[0], (size_t)(n_tiles + 32) * sizeof(int)));
@@ -905,8 +909,11 @@ int launch_field_begin(nsfs_planner* h, int si, int sj) {
     long long fill_blocks = (n4 + 255) / 256;
     if (fill_blocks < 1) fill_blocks = 1;
     if (fill_blocks > (long long)h->sm_count * 8) fill_blocks = (long long)h->sm_count * 8;
-    field_fill_kernel<<<(int)fill_blocks, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, reinterpret_cast<float4*>(f.gx), f.gx, h->N, f.tile_key,
-                                                              f.tile_busy, f.tiles_x * f.tiles_y);
+    const bool bucket = h->opt_field_mode == 3;       // only the bucket solver keeps the second plane
+    if (bucket && !f.gx) NSFS_CUDA_TRY(h, cudaMalloc(&f.gx, (size_t)(h->N + 4) * sizeof(float)));
+    f.gx_ready = bucket;
+    field_fill_kernel<<<(int)fill_blocks, 256, 0, h->stream>>>(reinterpret_cast<float4*>(f.g), n4, f.g, bucket ? reinterpret_cast<float4*>(f.gx) : nullptr,
+                                                              f.gx, h->N, f.tile_key, f.tile_busy, f.tiles_x * f.tiles_y);
     field_seed_kernel<<<1, 32, 0, h->stream>>>(p, h->d_free, h->d_out_mask, si, sj);
     h->launches += 2;
     NSFS_CUDA_TRY(h, cudaGetLastError());
@@ -939,7 +946,8 @@ int launch_field_relax(nsfs_planner* h, float cap) {
     cudaMemsetAsync(d_prof, 0, 8 * 4100, h->stream);
     p.prof = d_prof;
 #endif
-    if (h->opt_field_mode == 3) {      // bucketed push expansion (field_bucket.cu)
+    if (h->opt_field_mode == 3 && f.gx_ready) {      // bucket-ordered tile solver (field_bucket.cu); a field begun under another
+                                                     // mode has no gx plane and stays on the pull solver
         int rc = launch_field_relax_bucket(h, p);
         if (rc != NSFS_OK) return rc;
         field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);

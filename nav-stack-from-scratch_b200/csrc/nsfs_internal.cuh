@@ -78,7 +78,8 @@ struct FieldParams {
 
 struct FieldWork {
     float*    g = nullptr;         // [N]
-    float*    gx = nullptr;        // [N] bucket kernel: value at the last expansion (1e5 = never)
+    float*    gx = nullptr;        // [N] bucket kernel: value at the last expansion (1e5 = never); allocated on first use
+    bool      gx_ready = false;    // the field in progress was begun with gx filled
     uint8_t*  pred = nullptr;      // [N]
     uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
     int*      list[2] = {nullptr, nullptr};
