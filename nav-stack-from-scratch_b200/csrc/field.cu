@@ -785,35 +785,47 @@ __global__ void __launch_bounds__(256) field_pending_kernel(const uint32_t* __re
 // fp32 sum, so equality is exact).  The reference keeps whichever tied parent its heap order met first; any
 // of them is a valid optimal predecessor (north_star: path validity exact, cost within 1e-5).
 __global__ void __launch_bounds__(256) field_pred_kernel(const float* __restrict__ g, const uint16_t* __restrict__ in_mask,
-                                                         const uint16_t* __restrict__ out_mask, int W, long long N, long long ks,
-                                                         long long count_lo, long long count_hi,
+                                                         const uint16_t* __restrict__ out_mask, int W, int N, int ks,
+                                                         int count_lo, int count_hi,
                                                          uint8_t* __restrict__ pred, int* __restrict__ counts) {
-    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride over the cells (N < 2^29: 32-bit keys); the reached count and the throw flag leave the block through ONE
+    // atomic each (one atomicAdd per warp on a single address made this kernel 6 ms on the 16384^2 map: the L2 serialises them)
+    __shared__ int s_reached, s_thrown;
+    if (threadIdx.x == 0) { s_reached = 0; s_thrown = 0; }
+    __syncthreads();
     int reached = 0, thrown = 0;
-    if (v < N) {
+    int off[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) off[d] = nb_di(d) * W + nb_dj(d);
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < N; v += gridDim.x * 256) {
         const float gv = g[v];
-        uint8_t pd = 255;
+        uint32_t pd = 255u;
         if (gv < kInfF) {
             const bool counted = v >= count_lo && v < count_hi;     // a row-partitioned shard counts its own rows only
-            reached = counted;
+            reached += counted;
             if (counted && (__ldg(out_mask + v) & kThrowBit)) thrown = 1;   // a reached cell is expanded; expanding this one throws
             if (v != ks) {
                 const uint32_t m = __ldg(in_mask + v);
 #pragma unroll
                 for (int d = 7; d >= 0; --d) {
                     if (!((m >> d) & 1u)) continue;
-                    const float cand = g[v - nb_off(d, W)] + (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f);
-                    if (cand == gv) pd = (uint8_t)d;
+                    const float cand = g[v - off[d]] + (((m >> (8 + d)) & 1u) ? kSqrt2F : 1.0f);
+                    if (cand == gv) pd = (uint32_t)d;
                 }
             }
         }
-        pred[v] = pd;
+        pred[v] = (uint8_t)pd;
     }
-    const uint32_t rb = __ballot_sync(0xffffffffu, reached);
-    const uint32_t tb = __ballot_sync(0xffffffffu, thrown);
+    reached = __reduce_add_sync(0xffffffffu, reached);
+    thrown = __reduce_or_sync(0xffffffffu, (unsigned)thrown);
     if ((threadIdx.x & 31) == 0) {
-        if (rb) atomicAdd(counts + 5, __popc(rb));
-        if (tb) atomicOr(counts + 4, 1);
+        if (reached) atomicAdd(&s_reached, reached);
+        if (thrown) atomicOr(&s_thrown, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_reached) atomicAdd(counts + 5, s_reached);
+        if (s_thrown) atomicOr(counts + 4, 1);
     }
 }
 
@@ -1033,8 +1045,10 @@ int launch_field_finish(nsfs_planner* h) {
     const long long ks = f.src_i >= 0 ? (long long)f.src_i * h->W + f.src_j : -1;
     const long long lo = (long long)(h->opt_count_row_lo > 0 ? h->opt_count_row_lo : 0) * h->W;
     const long long hi = h->opt_count_row_hi > 0 ? (long long)h->opt_count_row_hi * h->W : h->N;
-    field_pred_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f.g, h->d_in_mask, h->d_out_mask, h->W, h->N, ks, lo, hi,
-                                                                             f.pred, f.counts);
+    long long blocks = (h->N + 255) / 256;
+    if (blocks > (long long)h->sm_count * 16) blocks = (long long)h->sm_count * 16;      // 8 resident blocks per SM, two waves
+    field_pred_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(f.g, h->d_in_mask, h->d_out_mask, h->W, (int)h->N, (int)ks, (int)lo, (int)hi,
+                                                               f.pred, f.counts);
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;
