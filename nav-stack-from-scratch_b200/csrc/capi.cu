@@ -100,6 +100,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
         rc = ensure_scratch(h, 1 << 16);
     } while (0);
     if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
+    if (const char* e = getenv("NSFS_FIELD_FENCE")) h->opt_field_fence = atoi(e);
     if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
     *out = h;
     return NSFS_OK;
@@ -804,6 +805,7 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_early")) { h->opt_field_early = value; return NSFS_OK; }
+    if (!strcmp(key, "field_fence")) { h->opt_field_fence = value; return NSFS_OK; }
     if (!strcmp(key, "field_merge")) { h->opt_field_merge = value; return NSFS_OK; }
     if (!strcmp(key, "field_sched_ns")) { h->opt_field_sched_ns = value; return NSFS_OK; }
     if (!strcmp(key, "field_gate")) { h->opt_field_gate = value; return NSFS_OK; }

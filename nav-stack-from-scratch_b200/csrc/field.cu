@@ -135,6 +135,15 @@ __global__ void __launch_bounds__(256) field_inject_kernel(FieldParams p, long l
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(improved, __popc(b));
 }
 
+// Key post with release semantics: orders this thread's earlier stores, and those of other threads it synchronised with
+// (__syncwarp / __syncthreads), before the key: MEMBAR.ALL.GPU + ATOMG, against MEMBAR.SC.GPU + CCTL.IVALL (an L1 invalidate)
+// + ATOMG for __threadfence() followed by a relaxed atomicMin.  Message passing needs no more than release / acquire.
+__device__ __forceinline__ uint32_t atomic_min_release(uint32_t* addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.release.gpu.global.min.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 // Relax one tile to its local fixed point (under the band limit thr).
 //
 // Inside the tile the warps run ASYNCHRONOUSLY: there is no block barrier per sweep.  Each warp owns four sub-blocks
@@ -291,7 +300,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                                 for (int qq = 0; qq < SB_PER_WARP; ++qq) if (qq == q) gk = key[qq];
                                 if (gk >= 0) __stcg(p.g + gk, vq);
                             }
-                            __threadfence();
+                            if (!p.light) __threadfence();
                             __syncwarp();
                             if (lane < 9 && lane != 4) {
                                 const int dy = lane / 3 - 1, dx = lane % 3 - 1;
@@ -302,7 +311,8 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                                 const int tdy = sy < 0 ? -1 : (sy >= SB_Y ? 1 : 0), tdx = sx < 0 ? -1 : (sx >= SB_X ? 1 : 0);
                                 const int ny = ty + tdy, nx = tx + tdx;
                                 if (need && (tdy || tdx) && ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
-                                    const uint32_t old = atomicMin(p.tile_key + ny * p.tiles_x + nx, kmin);
+                                    uint32_t* kp = p.tile_key + ny * p.tiles_x + nx;
+                                    const uint32_t old = p.light ? atomic_min_release(kp, kmin) : atomicMin(kp, kmin);
                                     if (old > p.cap && kmin <= p.cap) atomicAdd(p.gcount, 1);
                                 }
                             }
@@ -514,9 +524,14 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         if (tx == p.tiles_x - 1) post(c0 + lx == W - 1, 9);          // flat-key wrap: (r, W-1) feeds (r..r+2, 0)
         if (tx == 0 && sx == 0) post(lx == 0, 10);                    // flat-key wrap: (r, 0) feeds (r-2..r, W-1)
     }
-    if (ASYNC_TILES && (p.peer_g[0] || p.peer_g[1])) __threadfence_system();   // ... also on the neighbour GPU
-    else __threadfence();  // the improved cells are visible before the keys that announce them
+    // The improved cells must be visible before the keys that announce them.  Only warp 0 posts keys, so only warp 0 fences:
+    // the block barrier orders every thread's stores before it, and a fence is cumulative over what happened before it
+    // (1 fence per visit instead of 32: __threadfence is MEMBAR.SC.GPU + an L1 invalidate on sm_100).
     __syncthreads();
+    if (tid < 32) {
+        if (ASYNC_TILES && (p.peer_g[0] || p.peer_g[1])) __threadfence_system();   // ... also on the neighbour GPU
+        else if (!p.light) __threadfence();
+    }
     int newly = 0;        // tiles this thread made pending: summed over warp 0 and folded into ONE update of the pending counter
     if (ASYNC_TILES && tid >= 16 && tid < 32) {
         // wake the neighbour shard's tiles that hold, or read as halo, the two rows just pushed: its rows R-3 .. R+4 lie in at
@@ -559,7 +574,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
             target = tile;
         }
         if (target >= 0 && m != kNoKey) {
-            const uint32_t old = atomicMin(p.tile_key + target, m);
+            const uint32_t old = p.light ? atomic_min_release(p.tile_key + target, m) : atomicMin(p.tile_key + target, m);
             if (ASYNC_TILES && old > p.cap && m <= p.cap) newly = 1;     // a tile became pending (within the cap)
         }
     }
@@ -888,6 +903,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.blk_min = reinterpret_cast<uint32_t*>(f.list[0]);       // the bulk-synchronous variant's tile list is free in the asynchronous ones
     p.gate = h->opt_field_gate > 0 ? (float)h->opt_field_gate : 0.f;
     p.early = h->opt_field_early == 2 ? 0 : 1;                // 0 / 1 = on (default), 2 = off
+    p.light = h->opt_field_fence == 1 ? 1 : 0;                // key posts as release atomics instead of __threadfence + atomicMin
     p.merge = h->opt_field_merge == 2 ? 0 : 1;
     p.sched_ns = h->opt_field_sched_ns > 0 ? (unsigned)h->opt_field_sched_ns : 400u;
     p.gcount = f.counts + 1;
@@ -1006,6 +1022,7 @@ int launch_field_relax_p2p(nsfs_planner* h) {
     p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
     p.dynamic = 0;
     p.merge = 0;
+    p.light = 0;            // peer posts need system scope: keep the fences
     p.early = 0;            // ghost rows are lowered with atomics by both sides; keep their publication at the end of the visit
     int per_sm = 0;
     NSFS_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_solve_async_kernel, FIELD_THREADS, 0));

@@ -67,6 +67,7 @@ struct FieldParams {
     uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
     unsigned sched_ns;    // back-off of a block that owns no pending tile
     int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
+    int light;            // 1: key posts are release atomics (MEMBAR.ALL.GPU) instead of __threadfence (MEMBAR.SC.GPU + L1 invalidate) + atomicMin
     int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
     float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
     int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
@@ -160,6 +161,7 @@ struct nsfs_planner {
     long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
     long long opt_field_idle_ns = 0;    // 0 = default (1000)
     long long opt_field_alpha = -1;     // percent; < 0 = default (50); bulk-synchronous variant only
+    long long opt_field_fence = 0;      // 0 = __threadfence before key posts, 1 = release atomics (lighter fence, no L1 invalidate)
     long long opt_field_early = 0;      // post border changes to neighbouring tiles during a visit (cut-through): 0 / 1 = on, 2 = off
     long long opt_field_merge = 0;      // a visit absorbs posts that arrive for its own tile before it ends: 0 / 1 = on, 2 = off
     long long opt_field_sched_ns = 0;   // back-off of a block with no pending tile (0 = default 400)
