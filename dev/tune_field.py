@@ -16,13 +16,15 @@ alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
 dins = [int(x) for x in os.environ.get('DINS', '12').split(',')]
 groups = [int(x) for x in os.environ.get('TGROUPS', '0').split(',')]
 gates = [int(x) for x in os.environ.get('GATES', '0').split(',')]
-P.set_option('field_early', int(os.environ.get('EARLY', '0')))   # 0/1 on, 2 off
+earlies = [int(x) for x in os.environ.get('EARLY', '0').split(',')]   # 0/1 on, 2 off
+merges = [int(x) for x in os.environ.get('MERGE', '0').split(',')]    # 0/1 on, 2 off
+fences = [int(x) for x in os.environ.get('FENCE', '0').split(',')]    # 1: release-atomic key posts
 P.set_option('field_sched_ns', int(os.environ.get('SCHED', '0')))
-P.set_option('field_merge', int(os.environ.get('MERGE', '0')))   # 0/1 on, 2 off
 waits = [int(x) for x in os.environ.get('WAITS', '200').split(',')]
 for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, alphas, idles, dins, waits):
-  for grp, gate in itertools.product(groups, gates):
+  for grp, gate, early, merge, fence in itertools.product(groups, gates, earlies, merges, fences):
     P.set_option('field_groups', grp); P.set_option('field_gate', gate)
+    P.set_option('field_early', early); P.set_option('field_merge', merge); P.set_option('field_fence', fence)
     P.set_option('field_delta_in', din); P.set_option('field_wait_ns', wait)
     P.set_option('field_idle_ns', idle)
     P.set_option('field_alpha', alpha)
@@ -35,4 +37,4 @@ for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, al
     g = P.field(src)['g']
     if ref is None: ref = g
     same = np.array_equal(ref, g)
-    print(f"gate {gate} groups {grp} din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)
+    print(f"early {early} merge {merge} fence {fence} gate {gate} groups {grp} din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)

@@ -255,6 +255,7 @@ int nsfs_check_trajectory(nsfs_t* h, int n, const int32_t* ij, int t_id, int* sa
     const int last = single ? 0 : t_id;
     *safe = 1; *bad_idx = -1;
     if (last < 0) return NSFS_OK;                                                   // the loop body never runs
+    if (last >= n) return NSFS_E_RANGE;                                             // trajectory_.at(t_id) is the first thing the loop does
     const size_t in_b = align_up((size_t)n * 8, 256);
     if ((rc = ensure_scratch(h, in_b + 256)) != NSFS_OK) return rc;
     char* d = (char*)h->d_scratch;
