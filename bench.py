@@ -619,7 +619,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=33152, help="queries per step per GPU (c4): two waves of the 16 576 query slots (28 warps x 4 teams x 148 SMs)")
+    ap.add_argument("--batch", type=int, default=65536, help="queries per step per GPU (c4): the 65 536 queries BASELINE names, about four waves of the 16 576 query slots (28 warps x 4 teams x 148 SMs)")
     ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "rounds"],
                     help="c5 at N > 1: p2p = shards post boundary rows into each other's memory over NVLink from inside the solve "

@@ -101,6 +101,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
     } while (0);
     if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
     if (const char* e = getenv("NSFS_FIELD_FENCE")) h->opt_field_fence = atoi(e);
+    if (const char* e = getenv("NSFS_SEARCH_ORDER")) h->opt_search_order = atoi(e);
     if (const char* e = getenv("NSFS_MAX_SLOTS")) h->opt_max_slots = atoll(e);    // warps of query slots (experiments)
     if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
     *out = h;
@@ -790,6 +791,7 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
     if (!strcmp(key, "team_heap_cap")) { h->opt_team_heap_cap = value; team_free(h); return NSFS_OK; }
     if (!strcmp(key, "search_kernel")) { h->opt_search_kernel = value; return NSFS_OK; }
+    if (!strcmp(key, "search_order")) { h->opt_search_order = value; return NSFS_OK; }
     if (!strcmp(key, "graph")) {                            // 0 reference quirk graph, 1 textbook 8-connected grid: rebuild the edge masks
         if (value != 0 && value != 1) return NSFS_E_ARG;
         if (h->opt_graph == value) return NSFS_OK;

@@ -119,6 +119,8 @@ struct TeamWork {
     unsigned long long* heap = nullptr;
     uint32_t* epoch = nullptr;
     int*      work_counter = nullptr;
+    int32_t*  order = nullptr;     // start order of a batch larger than the slots (longest expected query first)
+    int       order_cap = 0;
 };
 
 }  // namespace nsfs
@@ -154,6 +156,7 @@ struct nsfs_planner {
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
+    long long opt_search_order = 0;     // batches larger than the slots: 0 / 1 = start the longest expected queries first, 2 = input order
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
     long long opt_field_inner = 0;      // 0 = default (16)
     long long opt_field_delta = 0;      // 0 = default (128)

@@ -44,6 +44,7 @@ struct TeamParams {
     int mode;
     int nq;
     const int32_t* q;             // {si, sj, gi, gj} per query
+    const int32_t* order;         // order[k] = the k-th query to start (longest expected first), or nullptr = input order
     int32_t* status;
     double* g_goal;
     int32_t* path_len;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
             if (fetch) {
                 if (q >= p.nq) phase = PH_DONE;
                 else {
-                    qi = q;
+                    qi = p.order ? p.order[q] : q;
                     ++epoch;
                     const int si = p.q[4 * qi], sj = p.q[4 * qi + 1];
                     gi = p.q[4 * qi + 2]; gj = p.q[4 * qi + 3];
@@ -324,6 +325,57 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
     if (have_slot && tl == 0) p.epoch[slot] = epoch;
 }
 
+// ---- start order ---------------------------------------------------------------------------------------------------------
+// The slots fetch queries from one counter, so a launch lasts until the query that STARTED last has finished, and the work per
+// query spans 200 .. 900 000 expansions (C4).  Longest-expected-first keeps the tail short.  Expected work: for Djikstra the
+// Chebyshev distance start -> goal; for Astar a linear form in |di|, |dj|, their maximum and the three terms the reference's
+// slipped heuristic brings in (h looks at the node's ROW only: |gj - gi| = h(goal) inflates the search, |gj - si| and |sj - si|
+// shrink it), fitted on 320 C4 queries against the reference's own settled counts: Spearman rank correlation 0.98 there and
+// 0.95 - 0.97 on other maps, sizes, densities and cost mode fg (0.60 - 0.85 for the distance alone).
+// One block: histogram of 1024 buckets in shared memory, exclusive scan, scatter.  Only the ORDER of starting changes; every
+// query is still replayed on its own and written to its own output index.
+__global__ void __launch_bounds__(1024) team_order_kernel(const int32_t* __restrict__ q, int nq, int span, int astar, int32_t* __restrict__ order) {
+    __shared__ int s_cnt[1024];
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    s_cnt[tid] = 0;
+    __syncthreads();
+    const long long full = (astar ? 1500ll : 1ll) * (span > 0 ? span : 1);
+    auto bucket = [&](int k) {
+        const int si = q[4 * k], sj = q[4 * k + 1], gi = q[4 * k + 2], gj = q[4 * k + 3];
+        const long long di = abs(gi - si), dj = abs(gj - sj), ch = di > dj ? di : dj;
+        long long e = ch;
+        if (astar) e = 147 * di + 219 * dj + 530 * ch + 587 * (long long)abs(gj - gi) - 232 * (long long)abs(gj - si) - 180 * (long long)abs(sj - si);
+        const long long d = e * 1023 / full;
+        return 1023 - (int)(d < 0 ? 0 : (d > 1023 ? 1023 : d));      // bucket 0 = the longest
+    };
+    for (int k = tid; k < nq; k += 1024) atomicAdd(&s_cnt[bucket(k)], 1);
+    __syncthreads();
+    // exclusive scan over the 1024 counts: warp scans, then the warp totals
+    const int c = s_cnt[tid];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    s_cnt[tid] = s_warp[warp] + incl - c;                            // first output position of bucket tid
+    __syncthreads();
+    for (int k = tid; k < nq; k += 1024) order[atomicAdd(&s_cnt[bucket(k)], 1)] = k;
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 int team_alloc(nsfs_planner* h, int want_slots) {
     TeamWork& s = h->team;
@@ -355,7 +407,7 @@ int team_alloc(nsfs_planner* h, int want_slots) {
 
 void team_free(nsfs_planner* h) {
     TeamWork& s = h->team;
-    cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter);
+    cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter); cudaFree(s.order);
     s = TeamWork();
 }
 
@@ -372,6 +424,17 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
     p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;
+    p.order = nullptr;
+    if (nq > p.slots && h->opt_search_order != 2) {                  // more queries than slots: start the long ones first
+        if (s.order_cap < nq) {
+            cudaFree(s.order); s.order = nullptr; s.order_cap = 0;
+            NSFS_CUDA_TRY(h, cudaMalloc(&s.order, (size_t)nq * sizeof(int32_t)));
+            s.order_cap = nq;
+        }
+        team_order_kernel<<<1, 1024, 0, h->stream>>>(d_q, nq, h->H > h->W ? h->H : h->W, algo == NSFS_ASTAR ? 1 : 0, s.order);
+        h->launches++;
+        p.order = s.order;
+    }
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
     const int block = TEAM_WARPS_PER_BLOCK * 32;
     const int per_block = TEAM_WARPS_PER_BLOCK * 4;
