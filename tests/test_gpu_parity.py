@@ -229,3 +229,38 @@ def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
         assert got["status"] == 0 and np.array_equal(got["g"], want["g"]) and np.array_equal(got["pred"], want["pred"]), opts
         assert got["reached"] == want["reached"]
     P.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,mode", [("astar", "f"), ("astar", "fg"), ("djikstra", "g")])
+def test_batch_larger_than_the_slots_and_its_start_order(gpu_lib, oracle_mod, algo, mode):
+    """A batch with more queries than slots runs in waves: the slots fetch queries from one counter, in the order
+    team_order_kernel laid out (longest expected query first).  Only the starting order changes: status, cost, settled count
+    and path of every query are those of the unconstrained run, of the input-order run, and (sampled) of the oracle; the
+    order actually used is a permutation that puts far-apart pairs first."""
+    infl, lo = mapgen.synth_map(96, 128, 0.12, 77)
+    qs = mapgen.sample_queries(infl, lo, 150, 77)
+    qs[3, 2:] = qs[3, :2]                                                     # start == goal
+    qs[4, 2:] = mapgen.sample_blocked_interior(infl, lo, 1, 77)[0]            # unreachable goal
+    qs[5] = (-1, 0, 5, 5)                                                     # bad start: reported, the batch goes on
+    P = gpu_lib.Planner(96, 128)
+    P.set_map(infl, lo)
+    P.set_option("search_kernel", 2)
+    free = P.plan_batch(algo, mode, qs, path_cap=700)                         # 150 slots: everything in flight at once
+    P.set_option("max_slots", 2)                                              # 2 warps = 8 slots: 19 waves
+    ordered = P.plan_batch(algo, mode, qs, path_cap=700)
+    P.set_option("search_order", 2)                                           # the same waves in input order
+    plain = P.plan_batch(algo, mode, qs, path_cap=700)
+    for got in (ordered, plain):
+        assert np.array_equal(got["status"], free["status"]) and np.array_equal(got["settled"], free["settled"])
+        assert np.array_equal(got["path_len"], free["path_len"]) and np.array_equal(got["paths"], free["paths"])
+        assert np.array_equal(got["g_goal"], free["g_goal"])
+        assert got["stats"]["pops"] == free["stats"]["pops"] and got["stats"]["pushes"] == free["stats"]["pushes"]
+    assert free["status"][5] != 0 and (free["status"][np.arange(150) != 5] == 0).all()
+    O = oracle_mod.Oracle(infl, lo)
+    A = {"astar": oracle_mod.ASTAR, "djikstra": oracle_mod.DJIKSTRA}[algo]
+    for t in (0, 3, 4, 17, 77, 149):
+        o = O.plan(A, mode, qs[t, :2], qs[t, 2:])
+        n = len(o["path"])
+        assert ordered["path_len"][t] == n and np.array_equal(ordered["paths"][t][:n], o["path"]) and ordered["settled"][t] == o["settled"]
+    P.close()
