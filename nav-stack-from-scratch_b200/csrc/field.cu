@@ -53,6 +53,44 @@ constexpr int SCOL0 = 4;               // smem column of tile column 0 (halo col
 constexpr int SROWS = TS + 2;
 
 
+// Which sub-blocks a warp owns.  The wavefront is a line through the tile, and only the sub-blocks on it have work: the more
+// warps those sub-blocks belong to, the more of the front advances at once.
+//   0: warp w owns sub-blocks w, w + 32, w + 64, w + 96 (a COLUMN of 16 sub-blocks falls on 4 warps; two sub-blocks of one warp
+//      are 16 cells apart)
+//   1: a 2 x 2 group of adjacent sub-blocks (fewest hand-overs between warps: measured 2.2x SLOWER - front parallelism is what counts)
+//   2: warp = (2 sy + b sx) mod 32 on the 16 x 8 grid of sub-blocks (default, b = 5): every row, column and 45-degree line of
+//      sub-blocks falls on distinct warps, two sub-blocks of one warp are >= 25 cells apart.  C2 solve 1.51 -> 1.39 ms, C5 48.4 -> 45.6 ms
+//      (b = 7, the lattice with the largest minimum distance, 32 cells: the same within noise).
+#ifndef NSFS_SB_BLOCKED
+#define NSFS_SB_BLOCKED ((NSFS_TS == 64 && NSFS_SB_PER_WARP == 4) ? 2 : 0)
+#endif
+#ifndef NSFS_SB_B
+#define NSFS_SB_B 5
+#endif
+__device__ __forceinline__ int sb_of(int warp, int q) {
+#if NSFS_SB_BLOCKED == 1
+    return (((warp >> 2) << 1) + (q >> 1)) * SB_X + ((warp & 3) << 1) + (q & 1);
+#elif NSFS_SB_BLOCKED == 2
+    // warp = (2 sy + 5 sx) mod 32 on the 16 x 8 grid of sub-blocks: any row (8), column (16) or 45-degree line of sub-blocks falls
+    // on distinct warps (w, w + 32 k of the default puts the 16 sub-blocks of a column on 4 warps)
+    const int sx = 2 * q + (warp & 1);
+    return (((warp - NSFS_SB_B * sx) & 31) >> 1) * SB_X + sx;
+#else
+    return warp + q * FIELD_WARPS;
+#endif
+}
+__device__ __forceinline__ int slot_of(int t) {              // index of sub-block t in s_due / s_flag (warp-major)
+#if NSFS_SB_BLOCKED == 1
+    const int by = t / SB_X, bx = t % SB_X;
+    return (((by >> 1) << 2) + (bx >> 1)) * SB_PER_WARP + ((by & 1) << 1) + (bx & 1);
+#elif NSFS_SB_BLOCKED == 2
+    const int sy = t / SB_X, sx = t % SB_X;
+    return ((2 * sy + NSFS_SB_B * sx) & 31) * SB_PER_WARP + (sx >> 1);
+#else
+    return (t % FIELD_WARPS) * SB_PER_WARP + t / FIELD_WARPS;
+#endif
+}
+
 __global__ void field_fill_kernel(float4* __restrict__ g4, long long n4, float* __restrict__ g, float4* __restrict__ gx4, float* __restrict__ gx,
                                   long long N, uint32_t* __restrict__ tile_key, int* __restrict__ tile_busy, int n_tiles) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,7 +221,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
     int soff[SB_PER_WARP];
 #pragma unroll
     for (int q = 0; q < SB_PER_WARP; ++q) {
-        const int sb = warp + q * FIELD_WARPS;
+        const int sb = sb_of(warp, q);
         const int ly = (sb / SB_X) * SBH + lr, lx = (sb % SB_X) * SBW + lc;
         const int r = r0 + ly, c = c0 + lx;
         soff[q] = (ly + 1) * SROW + SCOL0 + lx;
@@ -228,7 +266,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                 gmin = min(mymin, __reduce_min_sync(0xffffffffu, g4));
             }
             if (__uint_as_float(mymin) <= __uint_as_float(gmin) + p.delta_in) {
-                const int sb = warp + q * FIELD_WARPS;
+                const int sb = sb_of(warp, q);
                 if (counted_idle) {                                   // leave the idle count BEFORE consuming the key
                     if (lane == 0) atomicSub(s_ctl_, 1);
                     counted_idle = false;
@@ -281,7 +319,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                         const int sy = sb / SB_X + dy, sx = sb % SB_X + dx;
                         const int t = sy * SB_X + sx;
                         if (need && sy >= 0 && sy < SB_Y && sx >= 0 && sx < SB_X)
-                            atomicMin(s_due + (t % FIELD_WARPS) * SB_PER_WARP + t / FIELD_WARPS, kmin);
+                            atomicMin(s_due + slot_of(t), kmin);
                     }
                     if (ASYNC_TILES && p.early) {
                         // cut-through between tiles: a changed cell that faces another tile is published NOW (value, fence, key)
@@ -374,7 +412,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                                 for (int yy = 0; yy < 2; ++yy)
                                     for (int xx = 0; xx < 2; ++xx) {
                                         const int t2 = ((yy ? y1 : y0) / SBH) * SB_X + (xx ? x1 : x0) / SBW;
-                                        atomicMin(s_due + (t2 % FIELD_WARPS) * SB_PER_WARP + t2 / FIELD_WARPS, kb);
+                                        atomicMin(s_due + slot_of(t2), kb);
                                     }
                             }
                         }
@@ -398,7 +436,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
         const uint32_t due = reinterpret_cast<const volatile uint32_t*>(s_flag_)[warp];   // my four flags in one load
 #pragma unroll
         for (int q = 0; q < SB_PER_WARP && due != 0u; ++q) {
-            const int sb = warp + q * FIELD_WARPS;
+            const int sb = sb_of(warp, q);
             if (!((due >> (8 * q)) & 0xffu)) continue;                // warp-uniform
             if (counted_idle) {                                       // leave the idle count BEFORE consuming the flag
                 if (lane == 0) atomicSub(s_ctl_, 1);
@@ -439,7 +477,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
                     if (dx < 0) need &= 0x01010101u; else if (dx > 0) need &= 0x80808080u;
                     const int sy = sb / SB_X + dy, sx = sb % SB_X + dx;
                     const int t = sy * SB_X + sx;                     // flag slot = owner warp * 4 + its q
-                    if (need && sy >= 0 && sy < SB_Y && sx >= 0 && sx < SB_X) s_flag[(t % FIELD_WARPS) * SB_PER_WARP + t / FIELD_WARPS] = 1;
+                    if (need && sy >= 0 && sy < SB_Y && sx >= 0 && sx < SB_X) s_flag[slot_of(t)] = 1;
                 }
             }
             did = true;
@@ -485,7 +523,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, float
 #pragma unroll
     for (int q = 0; q < SB_PER_WARP; ++q) {
         const bool ch = (ever >> q) & 1u;
-        const int sb = warp + q * FIELD_WARPS;
+        const int sb = sb_of(warp, q);
         const int sy = sb / SB_X, sx = sb % SB_X;
         const int ly = sy * SBH + lr, lx = sx * SBW + lc;
         const uint32_t vb = ch ? __float_as_uint(v[q]) : kNoKey;
