@@ -200,6 +200,17 @@ int nsfs_any_angle(nsfs_t* h, int n, const int32_t* pts_ij, uint8_t* keep);
 int         nsfs_sync(nsfs_t* h);
 long long   nsfs_kernel_launches(const nsfs_t* h);   /* kernels launched through this handle so far */
 void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the handle */
+/* Options (all have working defaults; 0 = default unless stated):
+ *   "graph"          0 the reference's quirk graph | 1 textbook 8-connected grid; rebuilds the edge masks
+ *   "field_mode"     0 asynchronous pull solver | 1 bulk-synchronous rounds | 2 dynamic tile claiming | 3 bucket-ordered solver
+ *   "field_delta", "field_inner", "field_idle_ns", "field_wait_ns", "field_sched_ns", "field_early", "field_merge",
+ *   "field_gate", "field_groups", "field_delta_in", "field_alpha", "field_fence"   scheduling knobs of the field solvers
+ *                    (same bits whatever they are set to; profiles/r01_field_solve_ncu.md says what each measured)
+ *   "search_kernel"  0 auto | 1 one query per warp | 2 four queries per warp;   "search_order"  2 = start a batch in input order
+ *   "max_slots", "heap_cap", "team_heap_cap"   query slots (in warps) and open-list capacity per slot
+ *   "active_row_lo/hi", "count_row_lo/hi"      row windows of a shard (see the row-partitioned field above)
+ * Environment overrides read by nsfs_create (experiments / running the test-suite per solver): NSFS_FIELD_MODE, NSFS_FIELD_FENCE,
+ * NSFS_SEARCH_ORDER, NSFS_MAX_SLOTS. */
 int         nsfs_set_option(nsfs_t* h, const char* key, long long value);
 const char* nsfs_strerror(int code);
 const char* nsfs_last_cuda_error(const nsfs_t* h);
