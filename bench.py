@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """bench.py — headline measurement of the B200 grid planner (one JSON line on stdout from rank 0).
 
-Workloads (SURVEY.md §8d / BASELINE.json configs; ``--workload``):
-  c2 (default)  Djikstra full cost-to-go field, 2048x2048 raw map p=0.10 seed 5, source = centre      [configs[1]]
-  c4            batched Astar "f" start/goal queries, 1024x1024 raw map p=0.10 seed 7                  [configs[3]]
-  c1            Astar "f" single queries, 384x384 inflated map seed 1 (latency)                        [configs[0]]
-  c3            ThetaStar, 4096x4096 raw map p=0.20 seed 9, 16 start/goal pairs run as one batch        [configs[2]]
-  c5            Djikstra field on the 16384x16384 raw map p=0.10 seed 11; with N > 1 ranks the map is
-                partitioned by row blocks and 2-row halos are exchanged over NCCL                      [configs[4]]
+Default (what the driver runs at every N): BASELINE config C4, STRONG scaling —
+  65 536 Astar "f" start/goal queries on the 1024x1024 raw map (p=0.10, seed 7), `query_slice` per rank, the packed map
+  broadcast once over NCCL, every rank the same share of the same workload, results gathered on rank 0.
+  metric planner_queries_per_s at every N.  The same line carries, under "extra":
+    c2   Djikstra full field 2048x2048 (Gcell-relax/s, p50 ms per field, plugin-path e2e pageable / pinned)   [rank 0]
+    c5   Djikstra full field 16384x16384, one handle at N = 1, row blocks + NVLink peer-to-peer posts at N > 1,
+         with a position-weighted checksum of g and pred that must equal the committed single-GPU one
 
-A step = one pass of the hot path over one batch of synthetic input: one field (c2, c5), one batch of ``--batch``
-queries (c4), one query (c1), the 16 queries (c3).  ``value`` is measured with inputs resident in HBM (device time
-of the step's kernels, CUDA events on the launching stream, L2 flushed between steps); ``e2e`` goes through the
-host-pointer C-ABI calls with host<->device copies (pinned host memory) inside the timed region.
+Other workloads for single measurements (``--workload``):
+  c2   Djikstra full cost-to-go field, 2048x2048 raw map p=0.10 seed 5, source = centre                 [configs[1]]
+  c1   Astar "f" single queries, 384x384 inflated map seed 1 (latency)                                  [configs[0]]
+  c3   ThetaStar, 4096x4096 raw map p=0.20 seed 9, the 16 sampler pairs run as one batch                [configs[2]]
+  c5   Djikstra field on the 16384x16384 raw map p=0.10 seed 11 (N > 1: row blocks, p2p or NCCL rounds) [configs[4]]
+  c4w  the C4 queries with 65 536 queries PER GPU (weak scaling; round-1 lines)
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c1|c3|c5] [--impl ours|reference]
-N > 1 is launched by torchrun (one rank per GPU, NCCL).  c2/c4/c1/c3: the packed map is broadcast once from rank 0 and
-the work units are independent per rank (no data-path collective; weak scaling).  c5: one field, strong scaling.
-Timing is the max over ranks.
+A step = one pass of the hot path over one batch of synthetic input.  ``value`` is measured with inputs resident in HBM
+(device time of the step's kernels, CUDA events on the launching stream, L2 flushed between steps); ``e2e`` goes through
+the reference-facing C++ child (GpuAstar::planBatch / GpuDjikstra::generatePath over the nsfsh_* shim) with the map in
+pageable std::vector<int> planes, host<->device copies inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ...] [--impl ours|reference]
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Timing is the max over ranks.
 """
 from __future__ import annotations
 
@@ -41,19 +46,36 @@ from nsfs import mapgen  # noqa: E402
 
 BYTES_PER_SETTLED = 9.125        # read g (4) + write g (4) + write predecessor (1) + occupancy bit (0.125)
 RELAX_PER_SETTLED = 8            # one settled cell = 8 cell-relaxations (reference loop astar.cpp:89)
+C4_TOTAL = 65536
+C5_SETTLED = 241537616           # reference Djikstra settled count on the C5 map (SURVEY.md §6 probe)
+C5_CRC_FILE = os.path.join(ROOT, "tests", "golden", "c5_field_checksum.json")
 
 WORKLOADS = {
     "c2": dict(H=2048, W=2048, p=0.10, seed=5, inflated=False, algo="djikstra",
                name="Djikstra full cost-to-go field, 2048x2048 raw map p_occ=0.10 seed 5, source = centre (C2)"),
     "c4": dict(H=1024, W=1024, p=0.10, seed=7, inflated=False, algo="astar",
-               name="batched Astar f start/goal queries, 1024x1024 raw map p_occ=0.10 seed 7 (C4)"),
+               name="batched 65,536 Astar f start/goal queries, 1024x1024 raw map p_occ=0.10 seed 7, sharded over the GPUs (C4)"),
+    "c4w": dict(H=1024, W=1024, p=0.10, seed=7, inflated=False, algo="astar",
+                name="batched Astar f start/goal queries, 1024x1024 raw map p_occ=0.10 seed 7, 65,536 per GPU (C4, weak)"),
     "c1": dict(H=384, W=384, p=0.005, seed=1, inflated=True, algo="astar",
                name="Astar f single query, 384x384 inflated map p_occ=0.005 seed 1 (C1)"),
     "c3": dict(H=4096, W=4096, p=0.20, seed=9, inflated=False, algo="thetastar",
-               name="ThetaStar f, 4096x4096 raw map p_occ=0.20 seed 9, 16 start/goal pairs as one batch (C3)"),
+               name="ThetaStar f, 4096x4096 raw map p_occ=0.20 seed 9, the 16 sampler start/goal pairs as one batch (C3)"),
     "c5": dict(H=16384, W=16384, p=0.10, seed=11, inflated=False, algo="djikstra",
                name="Djikstra full cost-to-go field, 16384x16384 raw map p_occ=0.10 seed 11, source = centre (C5)"),
 }
+
+
+def shared_config(workload):
+    """The SAME dict in both arms (the driver compares them): what is run; how each arm measures it is spelled out once."""
+    wl = WORKLOADS[workload]
+    cfg = {"workload": wl["name"],
+           "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: n/a",
+           "timing": "GPU arm: device time of each step's kernels (CUDA events on the launching stream), max over ranks; "
+                     "reference arm: steady_clock around the reference's own plan() calls on all host threads"}
+    if workload == "c4":
+        cfg["queries_per_step"] = "GPU arm: all 65,536, query_slice per rank; reference arm: a bounded sample of the same query stream per step"
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -100,6 +122,8 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
+            if len(self.rows) > 4000:                        # long runs: keep every other sample
+                self.rows = self.rows[::2]
 
     def mark_start(self):
         self.t0 = time.time()
@@ -148,22 +172,25 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def c3_queries(infl, lo, seed, n=16):
-    """The C3 pairs: starts from the sampler, goals re-drawn a few hundred cells away so a query stays in the seconds."""
-    starts = mapgen.sample_free_cells(infl, lo, n, seed + 1)
-    free = mapgen.free_mask(infl, lo)
-    H, W = infl.shape
-    R = 300
-    qs = np.zeros((n, 4), np.int32)
-    for t, s0 in enumerate(starts):
-        i0, j0 = int(np.clip(s0[0], R, H - R - 1)), int(np.clip(s0[1], R, W - R - 1))
-        g = mapgen.sample_cells(free[i0 - R:i0 + R, j0 - R:j0 + R], 1, seed + 100 + t)[0]
-        qs[t] = (s0[0], s0[1], i0 - R + g[0], j0 - R + g[1])
-    return qs
+    """The C3 pairs as BASELINE states them: 16 consecutive (start, goal) pairs of the free-cell sampler on the 4096^2 map."""
+    return mapgen.sample_queries(infl, lo, n, seed)
+
+
+def host_so():
+    """The C++ children the plugin-path e2e goes through: the build against the reference's OWN grid_planner_core.h when it
+    exists (oracle/_ref/libnsfs_dropin.so), else the in-repo build against the interface mirror."""
+    p = os.path.join(ROOT, "oracle", "_ref", "libnsfs_dropin.so")
+    return (p, "GridPlannerCore children built against the reference's own headers (libnsfs_dropin.so)") if os.path.exists(p) else \
+        (None, "GridPlannerCore children built against the interface mirror (libnsfs_planners.so)")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -180,21 +207,21 @@ def reference_arm(args):
         return
     wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    note = None
     if args.workload == "c5":
-        # 153 s per field on one core: the bounded sample is the same generator at 1/16 of the area
-        H = W = 4096
-        note = "bounded sample: the C5 generator (p_occ=0.10, seed 11) at 4096x4096, one full field per host thread"
-    else:
-        H, W = wl["H"], wl["W"]
+        # one full field is 153 s and ~13 GB on one core and a field cannot use a second core: K + W of them do
+        # not fit the run's time limit.  No shrunken stand-in is reported as if it were C5.
+        emit({"impl": "reference", "unavailable": "C5 unmeasured here: one 16384^2 Djikstra::plan field takes ~153 s on one host core "
+                                                  "(SURVEY.md §6); the default arm (C4) carries the reference comparison"})
+        return
+    H, W = wl["H"], wl["W"]
     infl, lo = mapgen.synth_map(H, W, wl["p"], wl["seed"], wl["inflated"])
     orc, impl, kind, have_ref = cpu_impl(infl, lo)
     times, units = [], 0
-    if args.workload in ("c2", "c5"):
-        # a step = `threads` independent full fields, one per host thread (a single field cannot use more than one core)
+    if args.workload == "c2":
+        # a step = `threads` independent full fields from the C2 source, one per host thread (a single field cannot use
+        # more than one core); every thread does the same unit of work
         threads = min(cores, 64) if have_ref else 1
-        srcs = mapgen.sample_free_cells(infl, lo, threads, wl["seed"] + 17)
-        srcs[0] = mapgen.field_source(infl, lo)
+        srcs = np.repeat(np.asarray([mapgen.field_source(infl, lo)], np.int32), threads, 0)
         for it in range(args.warmup + args.steps):
             if have_ref:
                 r = impl.field_batch(srcs, nthreads=threads)
@@ -206,60 +233,74 @@ def reference_arm(args):
                 times.append(sec); units += settled
         value = RELAX_PER_SETTLED * units / sum(times) / 1e9
         metric, unit = "gcell_relax_per_s", "Gcell-relax/s"
-        sample = note or f"{threads} full fields per step (one per host thread) on the C2 map, {args.steps} steps"
+        sample = f"{threads} full fields from the C2 source per step (one per host thread), {args.steps} steps"
     else:
         threads = cores if have_ref else 1
+        note = None
         if args.workload == "c3":
             qs = c3_queries(infl, lo, wl["seed"])
-            note = ("ThetaStar has no reference implementation (thetastar.cpp is empty): the reference's Astar f + "
-                    "post_process_path on the same 16 pairs is the nearest reference behaviour")
+            note = ("ThetaStar has no reference implementation (thetastar.cpp is empty): the reference's Astar f on the same 16 "
+                    "pairs is the nearest reference behaviour")
+        elif args.workload in ("c4", "c4w"):
+            # bounded sample of the SAME query stream: 4 queries per host thread per step (~0.14 s each), a fresh slice every step
+            per_step = 4 * threads
+            allq = mapgen.sample_queries(infl, lo, per_step * (args.warmup + args.steps), wl["seed"])
+            qs = None
         else:
-            qs = mapgen.sample_queries(infl, lo, max(cores, 8) if args.workload == "c4" else 8, wl["seed"])
-        nq = len(qs)
+            qs = mapgen.sample_queries(infl, lo, 8 * threads, wl["seed"])
         for it in range(args.warmup + args.steps):
+            q = allq[it * per_step:(it + 1) * per_step] if qs is None else qs
             if have_ref:
-                sec = impl.plan_batch(0, "f", qs, nthreads=threads)["seconds"]
+                sec = impl.plan_batch(0, "f", q, nthreads=threads)["seconds"]
             else:
                 t0 = time.perf_counter()
-                for q in qs:
-                    impl.plan(0, "f", q[:2], q[2:])
+                for one in q:
+                    impl.plan(0, "f", one[:2], one[2:])
                 sec = time.perf_counter() - t0
             if it >= args.warmup:
-                times.append(sec); units += nq
+                times.append(sec); units += len(q)
         value = units / sum(times)
         metric, unit = "planner_queries_per_s", "queries/s"
-        sample = note or f"{nq} Astar f queries per step over {threads} host threads, {args.steps} steps"
+        sample = note or (f"{units // max(args.steps, 1)} Astar f queries of the C4 stream per step over {threads} host threads "
+                          f"(one planner instance per thread), {args.steps} steps")
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-        "scaling": "strong" if args.workload == "c5" else "weak",
+        "scaling": "strong" if args.workload == "c4" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "threads": threads},
+        "config": shared_config(args.workload),
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-def cpu_baseline(workload, infl, lo):
-    """Bounded sample of the same workload on the host cores (rank 0, N = 1 only)."""
+def cpu_baseline(workload, infl, lo, gpu_check=None):
+    """Bounded sample of the same workload on the host cores (rank 0, N = 1 only).  ``gpu_check`` (per-query arrays or the
+    field from the GPU arm) is compared with what the CPU planner returns: the bench line's own parity check."""
     wl = WORKLOADS[workload]
-    if workload == "c5":
-        infl, lo = mapgen.synth_map(4096, 4096, wl["p"], wl["seed"], False)
     orc, impl, kind, have_ref = cpu_impl(infl, lo)
-    if workload in ("c2", "c5"):
+    if workload == "c2":
         src = mapgen.field_source(infl, lo)
-        reps, secs, settled = (6 if workload == "c2" else 2), [], 0
+        reps, secs, settled, r = 4, [], 0, None
         for _ in range(reps):
             t0 = time.perf_counter(); r = impl.field(src); dt = time.perf_counter() - t0
             secs.append(r.get("seconds", dt)); settled = int(r["settled"])
         v = RELAX_PER_SETTLED * settled / float(np.median(secs)) / 1e9
-        what = "the C2 source" if workload == "c2" else "the centre of a 4096x4096 map from the C5 generator (1/16 of the area)"
-        return {"value": v, "unit": "Gcell-relax/s", "cores": 1, "kind": kind, "settled": settled,
-                "ms_per_field": 1e3 * float(np.median(secs)),
-                "sample": f"{reps} full Djikstra::plan fields from {what} on one core (median)"}
+        out = {"value": v, "unit": "Gcell-relax/s", "cores": 1, "kind": kind, "settled": settled,
+               "ms_per_field": 1e3 * float(np.median(secs)),
+               "sample": f"{reps} full Djikstra::plan fields from the C2 source on one core (median)"}
+        if gpu_check is not None:
+            g_ref = r["g"]
+            reach = g_ref < 1e5
+            g_gpu = gpu_check["g"].astype(np.float64)
+            same_reach = bool(np.array_equal(g_gpu < 1e5, reach))
+            rel = float((np.abs(g_gpu - g_ref)[reach] / np.maximum(g_ref[reach], 1.0)).max())
+            out["parity_checked"] = {"reachability_identical": same_reach, "max_rel_cost_error": rel, "bar": 1e-5,
+                                     "ok": bool(same_reach and rel <= 1e-5 and gpu_check["reached"] == settled)}
+        return out
     if workload == "c3":
-        qs = c3_queries(infl, lo, wl["seed"])[:6]
+        qs = c3_queries(infl, lo, wl["seed"])[:4]
         O = orc.Oracle(infl, lo)
         secs_t, secs_a = [], []
         for q in qs:
@@ -271,21 +312,30 @@ def cpu_baseline(workload, infl, lo):
                 "reference_astar_f_p50_ms": 1e3 * float(np.median(secs_a)), "reference_astar_kind": kind,
                 "sample": f"{len(qs)} of the 16 C3 pairs, one at a time on one core: the ThetaStar restatement (no reference "
                           "implementation exists) and, beside it, the reference's Astar f on the same pairs"}
-    nq = 64 if workload == "c4" else 200
+    nq = 64 if workload in ("c4", "c4w") else 200
     qs = mapgen.sample_queries(infl, lo, nq, wl["seed"])
-    secs = []
+    secs, res = [], []
     for q in qs:
         t0 = time.perf_counter(); r = impl.plan(0, "f", q[:2], q[2:]); dt = time.perf_counter() - t0
-        secs.append(r.get("seconds", dt))
-    return {"value": nq / float(np.sum(secs)), "unit": "queries/s", "cores": 1, "kind": kind,
-            "p50_ms": 1e3 * float(np.median(secs)), "p90_ms": 1e3 * float(np.percentile(secs, 90)),
-            "sample": f"{nq} Astar::plan f queries one at a time on one core"}
+        secs.append(r.get("seconds", dt)); res.append(r)
+    out = {"value": nq / float(np.sum(secs)), "unit": "queries/s", "cores": 1, "kind": kind,
+           "p50_ms": 1e3 * float(np.median(secs)), "p90_ms": 1e3 * float(np.percentile(secs, 90)),
+           "sample": f"the first {nq} queries of the workload, Astar::plan f one at a time on one core"}
+    if gpu_check is not None:
+        g = np.array([r["g_goal"] for r in res]); st = np.array([r["settled"] for r in res]); pl = np.array([len(r["path"]) for r in res])
+        gg = gpu_check["g_goal"][:nq]
+        ok = bool(np.array_equal(gpu_check["settled"][:nq], st) and np.array_equal(gpu_check["path_len"][:nq], pl)
+                  and np.all(np.abs(gg - g) <= 1e-12 * np.maximum(np.abs(g), 1.0)) and np.all(gpu_check["status"][:nq] == 0))
+        out["parity_checked"] = {"queries": nq, "settled_path_len_identical_cost_within_1e-12": ok, "ok": ok}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def ours_c5(args, torch, dist, rank, world, local, dev):
-    """One field on the 16384^2 map: a single handle at N = 1, row-block shards with NCCL halo exchange at N > 1."""
-    from nsfs import capi, sharded_field as sf
+def run_c5(torch, dist, rank, world, local, dev, steps, warmup, exchange="p2p", band=2048.0, want_e2e=True, want_fallback=True):
+    """One field on the 16384^2 map: a single handle at N = 1, row-block shards at N > 1 (peer-to-peer posts over NVLink inside
+    the solve kernel, or NCCL rounds).  Returns the measurements (every rank) — the caller formats them."""
+    from nsfs import sharded_field as sf
+    field_checksum = sf.field_checksum
 
     wl = WORKLOADS["c5"]
     H, W = wl["H"], wl["W"]
@@ -310,26 +360,24 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
             r = P.field_device((src[0] - a, src[1]))
             return dict(reached=r["reached"], rounds=1, kernel_ms=r["stats"]["main_kernel_ms"], dev_ms=r["stats"]["gpu_ms"],
                         visits=r["stats"]["tile_visits"])
-        if args.exchange == "p2p":
+        if exchange == "p2p":
             out = sf.solve_p2p(shard, src, dist, dev)
         else:
-            out = sf.solve_distributed(shard, src, dist, dev, band=args.band if args.band > 0 else None)
+            out = sf.solve_distributed(shard, src, dist, dev, band=band if band > 0 else None)
         return dict(reached=out["result"]["reached"], rounds=out["rounds"],
                     kernel_ms=sum(s["main_kernel_ms"] for s in shard.solver.stats),
                     dev_ms=sum(s["gpu_ms"] for s in shard.solver.stats) + out["result"]["stats"]["gpu_ms"],
                     visits=sum(s["tile_visits"] for s in shard.solver.stats))
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches0 = P.launches()
-    if sampler:
-        sampler.mark_start()
-    wall, kernel_ms, reached, last = 0.0, 0.0, 0, None
-    for _ in range(args.steps):
+    t_start = time.time()
+    wall, kernel_ms, reached, last, walls = 0.0, 0.0, 0, None, []
+    for _ in range(steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         if world > 1:
@@ -337,103 +385,369 @@ def ours_c5(args, torch, dist, rank, world, local, dev):
         t0 = time.perf_counter()
         last = step()
         torch.cuda.synchronize()
-        wall += time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        wall += dt; walls.append(dt)
         kernel_ms += last["kernel_ms"]; reached += last["reached"]
-    if sampler:
-        sampler.mark_stop()
+    t_stop = time.time()
     launches = P.launches() - launches0
+    # parity: the checksum of the owned rows of g and pred, summed over the ranks, against the committed single-GPU one
+    own = part.owned(rank)
+    g_rows = shard.owned_rows()
+    p_rows = shard.solver.pred_rows(shard.loc(own[0]), own[1] - own[0])
+    sg, sp = field_checksum(torch, g_rows, p_rows, own[0] * W)
     if world > 1:
         t = torch.tensor([wall, kernel_ms, float(reached), float(launches)], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         wall, kernel_ms, reached, launches = tmax[0].item(), tmax[1].item(), tsum[2].item(), int(tsum[3].item())
-    # e2e: upload this rank's int32 planes through the host-pointer call, solve, read the owned rows of g and pred back
-    pin_i, pin_l = torch.from_numpy(infl).pin_memory(), torch.from_numpy(lo).pin_memory()
-    own = part.owned(rank)
-    host_g = torch.empty((own[1] - own[0], W), dtype=torch.float32).pin_memory()
-    host_p = torch.empty((own[1] - own[0], W), dtype=torch.uint8).pin_memory()
+        # checksums as four 16-bit limbs each so that the all-reduce sum stays exact in int64
+        limbs = torch.tensor([(sg >> s) & 0xffff for s in (0, 16, 32, 48)] + [(sp >> s) & 0xffff for s in (0, 16, 32, 48)],
+                             dtype=torch.int64, device=dev)
+        dist.all_reduce(limbs, op=dist.ReduceOp.SUM)
+        lv = [int(x) for x in limbs.tolist()]
+        sg = sum(lv[k] << (16 * k) for k in range(4)) % (1 << 64)
+        sp = sum(lv[4 + k] << (16 * k) for k in range(4)) % (1 << 64)
+    out = dict(wall=wall, kernel_ms=kernel_ms, reached=reached, launches=launches, last=last, walls=walls, t_start=t_start,
+               t_stop=t_stop, checksum_g=f"{sg:016x}", checksum_pred=f"{sp:016x}", steps=steps, H=H, W=W, P=P, shard=shard,
+               part=part, infl=infl, lo=lo, src=src)
+    want = None
+    try:
+        want = json.load(open(C5_CRC_FILE))
+    except Exception:
+        pass
+    per_field = reached / steps
+    if want:
+        out["parity_checked"] = {"checksum_g": out["checksum_g"], "checksum_pred": out["checksum_pred"],
+                                 "committed": {k: want[k] for k in ("checksum_g", "checksum_pred")},
+                                 "settled": per_field, "reference_settled": C5_SETTLED,
+                                 "ok": bool(out["checksum_g"] == want["checksum_g"] and out["checksum_pred"] == want["checksum_pred"]
+                                            and int(per_field) == C5_SETTLED)}
+    else:
+        out["parity_checked"] = {"checksum_g": out["checksum_g"], "checksum_pred": out["checksum_pred"], "committed": None,
+                                 "settled": per_field, "reference_settled": C5_SETTLED, "ok": bool(int(per_field) == C5_SETTLED)}
+    if want_e2e:
+        # e2e: upload this rank's int32 planes through the host-pointer call, solve, read the owned rows of g and pred back
+        pin_i, pin_l = torch.from_numpy(infl).pin_memory(), torch.from_numpy(lo).pin_memory()
+        host_g = torch.empty((own[1] - own[0], W), dtype=torch.float32).pin_memory()
+        host_p = torch.empty((own[1] - own[0], W), dtype=torch.uint8).pin_memory()
 
-    def step_e2e():
-        P.set_map(pin_i.numpy(), pin_l.numpy())
-        r = step()
-        host_g.copy_(shard.owned_rows()); host_p.copy_(shard.solver.pred_rows(shard.loc(own[0]), own[1] - own[0]))
-        torch.cuda.synchronize()
-        return r["reached"]
+        def step_e2e():
+            P.set_map(pin_i.numpy(), pin_l.numpy())
+            r = step()
+            host_g.copy_(shard.owned_rows()); host_p.copy_(shard.solver.pred_rows(shard.loc(own[0]), own[1] - own[0]))
+            torch.cuda.synchronize()
+            return r["reached"]
 
-    e2e_steps = max(1, min(args.steps, 3))
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e2e_reached = sum(step_e2e() for _ in range(e2e_steps))
-    e2e_sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_sec, float(e2e_reached)], dtype=torch.float64, device=dev)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e_sec, e2e_reached = tmax[0].item(), tsum[1].item()
-    if rank != 0:
-        return
-    peak, peak_src = peaks()
-    settled = reached / args.steps
-    alg_bytes = BYTES_PER_SETTLED * settled / world            # per GPU: the dominant kernel of each rank covers its own rows
-    kernel_s = kernel_ms / args.steps * 1e-3
-    achieved = alg_bytes / kernel_s / 1e9
-    main_kernel = "field_solve_async_kernel"
-    line = {
-        "metric": "gcell_relax_per_s", "value": RELAX_PER_SETTLED * reached / wall / 1e9, "unit": "Gcell-relax/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "units_per_step": "1 field over all ranks",
-                   "partition": f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, " + ("peer-to-peer posts over NVLink inside the solve kernel (no rounds)" if args.exchange == "p2p" else f"NCCL send/recv + 1 all-reduce per round, band {args.band:g}") if world > 1 else "single handle",
-                   "l2": "flushed between timed steps (256 MiB fill)",
-                   "timing": "wall clock between cuda synchronize + barrier on both sides, max over ranks (the step spans several kernels, NCCL and host round control)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": main_kernel, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms / args.steps,
-                     "note": "per GPU: that rank's share of the settled cells over the summed time of its solve launches (max over ranks)"},
-        "e2e": {"value": RELAX_PER_SETTLED * e2e_reached / e2e_sec / 1e9, "unit": "Gcell-relax/s",
-                "h2d_bytes_per_step": int(2 * infl.size * 4 * world), "d2h_bytes_per_step": int(H * W * 5),
-                "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps},
-        "gpu_launches": launches, "clocks": sampler.finish() if sampler else None,
-        "extra": {"settled_per_field": settled, "exchange_rounds": last["rounds"], "tile_visits_rank0": last["visits"],
-                  "fields_per_s": args.steps / wall},
-    }
-    if world == 1:
+        e2e_steps = max(1, min(steps, 2))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_reached = sum(step_e2e() for _ in range(e2e_steps))
+        e2e_sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_sec, float(e2e_reached)], dtype=torch.float64, device=dev)
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            e2e_sec, e2e_reached = tmax[0].item(), tsum[1].item()
+        out.update(e2e_sec=e2e_sec, e2e_reached=e2e_reached, e2e_steps=e2e_steps,
+                   h2d=int(2 * infl.size * 4 * world), d2h=int(H * W * 5))
+    if want_fallback and world == 1:
         # C5 (ii): 1024 find_better_point calls from random non-free interior cells (replicas only: each search is local)
         bad = mapgen.sample_blocked_interior(infl, lo, 1024, wl["seed"])
         P.find_better_point_batch(bad[:64])
         fb = P.find_better_point_batch(bad)
-        line["extra"]["fallback_1024"] = {"queries_per_s": 1024 / (fb["stats"]["gpu_ms"] * 1e-3), "gpu_ms": fb["stats"]["gpu_ms"],
-                                          "settled": fb["stats"]["expansions"]}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline("c5", None, None)
+        out["fallback_1024"] = {"queries_per_s": 1024 / (fb["stats"]["gpu_ms"] * 1e-3), "gpu_ms": fb["stats"]["gpu_ms"],
+                                "settled": fb["stats"]["expansions"]}
+    return out
+
+
+def c5_summary(r, world, exchange):
+    """The C5 measurements as the dict that goes under extra["c5"] (default run) or into the c5 line."""
+    alg_bytes = BYTES_PER_SETTLED * (r["reached"] / r["steps"]) / world
+    peak, _ = peaks()
+    achieved = alg_bytes / (r["kernel_ms"] / r["steps"] * 1e-3) / 1e9
+    d = {"workload": WORKLOADS["c5"]["name"], "gcell_relax_per_s": RELAX_PER_SETTLED * r["reached"] / r["wall"] / 1e9,
+         "ms_per_field": 1e3 * r["wall"] / r["steps"], "p50_ms_per_field": 1e3 * float(np.median(r["walls"])), "steps": r["steps"],
+         "partition": (f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, " +
+                       ("peer-to-peer posts over NVLink inside the solve kernel (no rounds)" if exchange == "p2p" else "NCCL rounds"))
+         if world > 1 else "single handle",
+         "timing": "wall clock between cuda synchronize + barrier on both sides, max over ranks",
+         "solve_kernel_ms_per_field_max_rank": r["kernel_ms"] / r["steps"], "roofline_frac": achieved / peak,
+         "tile_visits_rank0": r["last"]["visits"], "parity_checked": r["parity_checked"]}
+    if "fallback_1024" in r:
+        d["fallback_1024"] = r["fallback_1024"]
+    if "e2e_sec" in r:
+        d["e2e_ms_per_field"] = 1e3 * r["e2e_sec"] / r["e2e_steps"]
+    return d
+
+
+def ours_c5(args, torch, dist, rank, world, local, dev):
+    sampler = ClockSampler(local) if rank == 0 else None
+    r = run_c5(torch, dist, rank, world, local, dev, args.steps, args.warmup, args.exchange, args.band)
+    if rank != 0:
+        return
+    sampler.t0, sampler.t1 = r["t_start"], r["t_stop"]
+    peak, peak_src = peaks()
+    alg_bytes = BYTES_PER_SETTLED * (r["reached"] / r["steps"]) / world            # per GPU: the dominant kernel of each rank covers its own rows
+    achieved = alg_bytes / (r["kernel_ms"] / r["steps"] * 1e-3) / 1e9
+    s = c5_summary(r, world, args.exchange)
+    line = {
+        "metric": "gcell_relax_per_s", "value": s["gcell_relax_per_s"], "unit": "Gcell-relax/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["ms_per_field"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(shared_config("c5"), units_per_step="1 field over all ranks", partition=s["partition"]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "field_solve_async_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": r["kernel_ms"] / r["steps"],
+                     "note": "per GPU: that rank's share of the settled cells over the summed time of its solve launches (max over ranks)"},
+        "e2e": {"value": RELAX_PER_SETTLED * r["e2e_reached"] / r["e2e_sec"] / 1e9, "unit": "Gcell-relax/s",
+                "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": 1e3 * r["e2e_sec"] / r["e2e_steps"], "steps": r["e2e_steps"]},
+        "gpu_launches": r["launches"], "clocks": sampler.finish(),
+        "extra": {"settled_per_field": r["reached"] / r["steps"], "exchange_rounds": r["last"]["rounds"],
+                  "tile_visits_rank0": r["last"]["visits"], "fields_per_s": r["steps"] / r["wall"],
+                  "parity_checked": r["parity_checked"], "fallback_1024": r.get("fallback_1024")},
+    }
     emit(line)
 
 
-def ours(args):
-    import torch
+# ---------------------------------------------------------------------------------------------------------------
+def extra_c2(torch, local, dev, steps=20, warmup=5, want_cpu=True):
+    """Rank 0: the C2 field line (device-timed, L2 flushed), the plugin-path e2e (GpuDjikstra::generatePath, field backend,
+    pageable and pinned MapData) and the parity of the field against the reference's own Djikstra::plan."""
+    from nsfs import capi, host as nhost
+
+    wl = WORKLOADS["c2"]
+    H, W = wl["H"], wl["W"]
+    infl, lo = mapgen.synth_map(H, W, wl["p"], wl["seed"], False)
+    src = mapgen.field_source(infl, lo)
+    P = capi.Planner(H, W, device=local)
+    P.set_map(infl, lo)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        P.field_device(src)
+    ms, kms, reached = [], [], 0
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        r = P.field_device(src)
+        ms.append(r["stats"]["gpu_ms"]); kms.append(r["stats"]["main_kernel_ms"]); reached = r["reached"]
+    peak, _ = peaks()
+    out = {"workload": wl["name"], "gcell_relax_per_s": RELAX_PER_SETTLED * reached * steps / (sum(ms) * 1e-3) / 1e9,
+           "ms_per_field": float(np.mean(ms)), "p50_ms_per_field": float(np.median(ms)), "steps": steps,
+           "solve_kernel_ms": float(np.mean(kms)), "settled": reached,
+           "roofline_frac": BYTES_PER_SETTLED * reached / (float(np.mean(kms)) * 1e-3) / 1e9 / peak,
+           "timing": "device time of the call's kernels (CUDA events on the handle's stream), L2 flushed between steps"}
+    # host-pointer C-ABI (pinned buffers): what round 1 reported as e2e
+    pin_i, pin_l = torch.from_numpy(infl).pin_memory(), torch.from_numpy(lo).pin_memory()
+    host_g = torch.empty((H, W), dtype=torch.float32).pin_memory(); host_p = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    st = capi.Stats()
+
+    def cabi():
+        P.set_map(pin_i.numpy(), pin_l.numpy())
+        assert P.L.nsfs_field(P.h, src[0], src[1], host_g.numpy().ctypes.data, host_p.numpy().ctypes.data, st) == 0
+
+    for _ in range(2):
+        cabi()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        cabi()
+    out["e2e_cabi_pinned_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    field = dict(g=host_g.numpy().copy(), reached=reached)
+    P.close()
+    # the call a GlobalPlanner makes: GpuDjikstra::generatePath (field backend) on a MapData with pageable std::vector<int> planes
+    so, what = host_so()
+    goal = tuple(int(x) for x in mapgen.sample_free_cells(infl, lo, 1, 99)[0])
+    try:
+        S = nhost.Session("djikstra", "g", infl, lo, backend="field", device=local, so_path=so)
+        for mode in ("every_call", "every_call_pinned", "on_notify"):
+            S.set_map_sync(mode)
+            for _ in range(2):
+                S.generate_path_idx(src, goal)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                r = S.generate_path_idx(src, goal)
+            out[f"e2e_generatePath_{mode}_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+        out["e2e_generatePath"] = (f"{what}; one Djikstra plan request = upload of both int32 planes from MapData's std::vector<int> "
+                                   "(every_call: pageable, the reference's contract; every_call_pinned: the same vectors page-locked once; "
+                                   "on_notify: no upload unless the map changed) + field + predecessor walk + post_process_path")
+        S.close()
+    except Exception as e:          # noqa: BLE001 — the line must still be printed
+        out["e2e_generatePath_error"] = repr(e)
+    if want_cpu:
+        out["cpu_baseline"] = cpu_baseline("c2", infl, lo, gpu_check=field)
+    return out
+
+
+def ours_c4(args, torch, dist, rank, world, local, dev):
+    """Default: the 65 536 C4 queries sharded over the ranks (strong scaling) + the C2 / C5 lines under extra."""
+    from nsfs import capi, host as nhost, sharded_queries as sq
+
+    wl = WORKLOADS["c4"]
+    H, W = wl["H"], wl["W"]
+    total = args.batch
+    P = capi.Planner(H, W, device=local)
+    infl, lo = mapgen.synth_map(H, W, wl["p"], wl["seed"], wl["inflated"])
+    if rank == 0:
+        d_infl = torch.from_numpy(infl).to(dev); d_lo = torch.from_numpy(lo).to(dev)
+        P.set_map_device(d_infl.data_ptr(), d_lo.data_ptr())
+    if world > 1:
+        sq.broadcast_packed_map(P, dist, dev, rank)               # N/4 bytes over NCCL, once
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    if rank == 0:
+        allq = mapgen.sample_queries(infl, lo, total, wl["seed"])
+        allq_t = torch.from_numpy(np.ascontiguousarray(allq)).to(dev)
+    else:
+        allq_t = torch.zeros((total, 4), dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.broadcast(allq_t, src=0)
+    a, b = sq.query_slice(total, world, rank)
+    myq = allq_t[a:b].contiguous()
+    nq = b - a
+    d_status = torch.zeros(nq, dtype=torch.int32, device=dev); d_g = torch.zeros(nq, dtype=torch.float64, device=dev)
+    d_len = torch.zeros(nq, dtype=torch.int32, device=dev); d_set = torch.zeros(nq, dtype=torch.int64, device=dev)
+
+    def step_resident():
+        st = P.plan_batch_device("astar", "f", nq, myq.data_ptr(), d_status.data_ptr(), d_g.data_ptr(), d_len.data_ptr(),
+                                 d_set.data_ptr(), want_stats=True)
+        return st, int(d_set.sum().item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for w in range(args.warmup):
+        st, _ = step_resident()
+        if rank == 0:
+            log(f"warm-up {w}: {st['gpu_ms']:.0f} ms for {nq} queries on this rank")
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = P.launches()
+    if sampler:
+        sampler.mark_start()
+    t_wall0 = time.perf_counter()
+    dev_ms, main_ms, settled_total, last_stats, per_step_ms = 0.0, 0.0, 0, None, []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        st, settled = step_resident()
+        dev_ms += st["gpu_ms"]; main_ms += st["main_kernel_ms"]; settled_total += settled; last_stats = st
+        per_step_ms.append(st["gpu_ms"])
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if sampler:
+        sampler.mark_stop()
+    launches = P.launches() - launches0
+    pops_rank = float(last_stats["pops"])
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([dev_ms, main_ms, float(settled_total), float(launches), pops_rank], dtype=torch.float64, device=dev)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dev_ms_max, main_ms_max, dev_ms_min = tmax[0].item(), tmax[1].item(), tmin[0].item()
+        settled_all, launches_all, pops_all = tsum[2].item(), int(tsum[3].item()), tsum[4].item()
+    else:
+        dev_ms_max, main_ms_max, dev_ms_min = dev_ms, main_ms, dev_ms
+        settled_all, launches_all, pops_all = float(settled_total), launches, pops_rank
+    gpu_results = dict(status=d_status.cpu().numpy(), g_goal=d_g.cpu().numpy(), path_len=d_len.cpu().numpy(), settled=d_set.cpu().numpy())
+    P.close()                                                      # the query slots (85 % of HBM) go back before the plugin-path leg
+    del P
+
+    # ---- e2e: the reference-facing C++ child (GpuAstar::planBatch over the nsfsh_* shim), pageable MapData, results gathered ----
+    so, what = host_so()
+    host_q = np.ascontiguousarray(myq.cpu().numpy())
+    S = nhost.Session("astar", "f", infl, lo, device=local, so_path=so)
+    pad = -(-total // world)                                       # NCCL gather wants equal shares: pad the last rows
+    packed = torch.zeros((pad, 4), dtype=torch.float64, device=dev)
+    gathered = [torch.zeros((pad, 4), dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def step_e2e():
+        r = S.plan_batch_idx(host_q)                               # uploads both planes from pageable vectors, queries in, results out
+        if world > 1:                                              # result gather on rank 0 (NCCL), then to the host
+            packed[:nq].copy_(torch.from_numpy(np.stack([r["status"].astype(np.float64), r["g_goal"], r["path_len"].astype(np.float64),
+                                                    r["settled"].astype(np.float64)], 1)))
+            dist.gather(packed, gathered, dst=0)
+            if rank == 0:
+                torch.cat(gathered).cpu()
+        return r
+
+    e2e_steps = max(1, min(args.steps, 2))
+    step_e2e()                                                     # allocates the session's own query slots
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    e2e_same = bool(np.array_equal(r_e2e["settled"], gpu_results["settled"]) and np.array_equal(r_e2e["g_goal"], gpu_results["g_goal"]))
+    S.close()
+    if world > 1:
+        t = torch.tensor([e2e_sec, 0.0 if e2e_same else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec, e2e_same = t[0].item(), t[1].item() == 0.0
+
+    # ---- the other two configs BASELINE names, under extra -----------------------------------------------------------------
+    extra_lines = {}
+    if not args.no_extra:
+        if rank == 0:
+            try:
+                extra_lines["c2"] = extra_c2(torch, local, dev, want_cpu=(world == 1 and not args.no_cpu_baseline))
+            except Exception as e:      # noqa: BLE001
+                extra_lines["c2"] = {"error": repr(e)}
+        if world > 1:
+            dist.barrier()
+        try:
+            r5 = run_c5(torch, dist, rank, world, local, dev, steps=3, warmup=2, exchange="p2p", want_e2e=False)
+            extra_lines["c5"] = c5_summary(r5, world, "p2p")
+            r5["shard"].solver.close()
+        except Exception as e:          # noqa: BLE001
+            extra_lines["c5"] = {"error": repr(e)}
+    if rank != 0:
+        return
+
+    peak, peak_src = peaks()
+    value = total * args.steps / (dev_ms_max * 1e-3)
+    alg_bytes = BYTES_PER_SETTLED * settled_all / (args.steps * world)          # per launch of the dominant kernel (one per rank and step)
+    achieved = alg_bytes / (main_ms_max / args.steps * 1e-3) / 1e9
+    line = {
+        "metric": "planner_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": shared_config("c4"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("search_team_kernel", nq), "kernel": "search_team_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": main_ms_max / args.steps,
+                     "note": "per GPU: 9.125 B x the reference-settled cells of that rank's queries over its kernel time (max over ranks)"},
+        "e2e": {"value": total * e2e_steps / e2e_sec, "unit": "queries/s",
+                "h2d_bytes_per_step": int(world * 2 * H * W * 4 + total * 16), "d2h_bytes_per_step": int(total * 24),
+                "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps,
+                "path": f"{what}: GpuAstar::planBatch on a MapData with pageable std::vector<int> planes (uploaded every call), "
+                        "queries from host memory, per-query results back to the host" + (", then gathered on rank 0 over NCCL" if world > 1 else ""),
+                "same_results_as_resident_path": e2e_same},
+        "gpu_launches": launches_all,
+        "clocks": sampler.finish() if sampler else None,
+        "extra": dict({"queries_per_gpu": nq, "map_broadcast": "NCCL, packed bit planes (N/4 bytes), once" if world > 1 else "n/a",
+                       "gcell_relax_per_s": RELAX_PER_SETTLED * settled_all / (dev_ms_max * 1e-3) / 1e9,
+                       "settled_per_query": settled_all / (total * args.steps), "pops_per_step": pops_all,
+                       "p50_ms_per_step": float(np.median(per_step_ms)), "slowest_rank_ms_per_step": dev_ms_max / args.steps,
+                       "fastest_rank_ms_per_step": dev_ms_min / args.steps,
+                       "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}, **extra_lines),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline("c4", infl, lo, gpu_check=gpu_results)
+    emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def ours_replicas(args, torch, dist, rank, world, local, dev):
+    """c2 / c1 / c3 / c4w: every rank runs the same unit of work on its own GPU (replicas; no data-path collective)."""
     from nsfs import capi, sharded_queries as sq
 
-    rank, world, local = dist_env()
-    guard_stdout()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if args.workload == "c5":
-        ours_c5(args, torch, dist, rank, world, local, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
     wl = WORKLOADS[args.workload]
     H, W = wl["H"], wl["W"]
     P = capi.Planner(H, W, device=local)
-
-    # ---- inputs: rank 0 packs the synthetic map; other ranks receive the two bit planes over NCCL ----------------
-    # (every rank also keeps the int32 host planes: the e2e leg uploads them through nsfs_set_map each step)
     infl, lo = mapgen.synth_map(H, W, wl["p"], wl["seed"], wl["inflated"])
     if rank == 0:
         d_infl = torch.from_numpy(infl).to(dev)
@@ -442,18 +756,10 @@ def ours(args):
     if world > 1:
         sq.broadcast_packed_map(P, dist, dev, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    field = None
 
-    # ---- per-rank work units ---------------------------------------------------------------------------------
     if args.workload == "c2":
-        if rank == 0:
-            srcs = mapgen.sample_free_cells(infl, lo, max(world, 1), wl["seed"] + 17)
-            srcs[0] = mapgen.field_source(infl, lo)
-            srcs_t = torch.from_numpy(srcs.astype(np.int32)).to(dev)
-        else:
-            srcs_t = torch.zeros((world, 2), dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.broadcast(srcs_t, src=0)
-        src = tuple(int(x) for x in srcs_t[rank].tolist())
+        src = mapgen.field_source(infl, lo)                             # the same source on every rank: the same unit of work
 
         def step_resident():
             r = P.field_device(src)
@@ -475,19 +781,12 @@ def ours(args):
         main_kernel = "field_solve_async_kernel"
     else:
         algo = wl["algo"]
-        per_step = {"c4": args.batch, "c1": 1, "c3": 16}[args.workload]
+        per_step = {"c4w": args.batch, "c1": 1, "c3": 16}[args.workload]
         nq = per_step
-        rotating = args.workload == "c1"                    # c1: a different query every step
-        total = nq * world * ((args.steps + args.warmup) if rotating else 1)
-        if rank == 0:
-            allq = c3_queries(infl, lo, wl["seed"], 16 * world) if args.workload == "c3" else mapgen.sample_queries(infl, lo, total, wl["seed"])
-            allq_t = torch.from_numpy(np.ascontiguousarray(allq)).to(dev)
-        else:
-            allq_t = torch.zeros((total, 4), dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.broadcast(allq_t, src=0)
-        a, b = sq.query_slice(total, world, rank)
-        myq = allq_t[a:b].contiguous()
+        rotating = args.workload == "c1"                    # c1: a different query every step (the same sequence on every rank)
+        total = nq * ((args.steps + args.warmup) if rotating else 1)
+        allq = c3_queries(infl, lo, wl["seed"], 16) if args.workload == "c3" else mapgen.sample_queries(infl, lo, total, wl["seed"])
+        myq = torch.from_numpy(np.ascontiguousarray(allq)).to(dev)
         per = myq.shape[0]
         d_status = torch.zeros(nq, dtype=torch.int32, device=dev); d_g = torch.zeros(nq, dtype=torch.float64, device=dev)
         d_len = torch.zeros(nq, dtype=torch.int32, device=dev); d_set = torch.zeros(nq, dtype=torch.int64, device=dev)
@@ -513,9 +812,8 @@ def ours(args):
             return int(r["settled"].sum())
 
         h2d, d2h = nq * 16, nq * (4 + 8 + 4 + 8)
-        main_kernel = "search_team_kernel" if args.workload == "c4" else ("search_team_kernel(batch)" if nq > 1 and algo != "thetastar" else "search_kernel")
+        main_kernel = "search_team_kernel" if args.workload == "c4w" else "search_kernel"
 
-    # ---- warm-up, then exactly K timed steps (device time of each step's kernels; L2 flushed between steps) ----
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step_resident()
@@ -549,7 +847,6 @@ def ours(args):
     else:
         dev_ms_max, main_ms_max, settled_all, launches_all = dev_ms, main_ms, float(settled_total), launches
 
-    # ---- e2e through the host-pointer API: every rank uploads its inputs and reads its results each step --------
     e2e_warm = 2 if args.workload in ("c2", "c1") else 0
     for _ in range(e2e_warm):
         step_e2e()
@@ -563,13 +860,14 @@ def ours(args):
         e2e_settled += step_e2e()
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
+    if args.workload == "c2":
+        field = dict(g=host_g.numpy().copy(), reached=int(e2e_settled / e2e_steps))
     if world > 1:
         t = torch.tensor([e2e_sec, float(e2e_settled)], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         e2e_sec, e2e_settled = tmax[0].item(), tsum[1].item()
     if rank != 0:
-        dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
@@ -586,31 +884,53 @@ def ours(args):
         e2e_value = world * nq * e2e_steps / e2e_sec
         extra = {"gcell_relax_per_s": RELAX_PER_SETTLED * settled_all / (dev_ms_max * 1e-3) / 1e9,
                  "settled_per_query": settled_all / (world * nq * args.steps), "batch": nq, "pops": last_stats["pops"],
-                 "los_checks": last_stats["los_checks"], "p50_ms_per_step": float(np.median(per_step_ms))}
+                 "los_checks": last_stats["los_checks"], "p50_ms_per_step": float(np.median(per_step_ms)),
+                 "p90_ms_per_step": float(np.percentile(per_step_ms, 90))}
     alg_bytes = BYTES_PER_SETTLED * settled_all / (args.steps * world)          # per launch of the dominant kernel
     achieved = alg_bytes / (main_ms_max / args.steps * 1e-3) / 1e9
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.workload == "c2" else "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "units_per_step_per_gpu": "1 field" if args.workload == "c2" else f"{nq} queries",
-                   "l2": "flushed between timed steps (256 MiB fill)", "map_broadcast": "NCCL, packed bit planes" if world > 1 else "n/a",
-                   "timing": "sum of per-step device time (CUDA events on the launching stream), max over ranks",
-                   "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
+        "config": dict(shared_config(args.workload), units_per_step_per_gpu="1 field" if args.workload == "c2" else f"{nq} queries",
+                       wall_ms_per_step_incl_flush=1e3 * t_wall / args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(main_kernel, nq), "kernel": main_kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": main_ms_max / args.steps},
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps},
+                "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps,
+                "path": "host-pointer C-ABI (nsfs_set_map + nsfs_field / nsfs_plan_batch), pinned host buffers"},
         "gpu_launches": launches_all,
         "clocks": sampler.finish() if sampler else None,
         "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, infl, lo)
+        line["cpu_baseline"] = cpu_baseline(args.workload, infl, lo, gpu_check=field)
     emit(line)
+
+
+def ours(args):
+    import torch
+
+    rank, world, local = dist_env()
+    guard_stdout()
+    dist = None
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    try:
+        if args.workload == "c5":
+            ours_c5(args, torch, dist, rank, world, local, dev)
+        elif args.workload == "c4":
+            ours_c4(args, torch, dist, rank, world, local, dev)
+        else:
+            ours_replicas(args, torch, dist, rank, world, local, dev)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
 
 
 def main():
@@ -618,16 +938,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=65536, help="queries per step per GPU (c4): the 65 536 queries BASELINE names, about four waves of the 16 576 query slots (28 warps x 4 teams x 148 SMs)")
-    ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1: cost units all shards advance per exchange round (0 = unbounded)")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=C4_TOTAL, help="c4: queries per step over ALL ranks (65 536 = BASELINE); c4w: per GPU")
+    ap.add_argument("--band", type=float, default=2048.0, help="c5 at N > 1 with --exchange rounds: cost units all shards advance per round (0 = unbounded)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "rounds"],
                     help="c5 at N > 1: p2p = shards post boundary rows into each other's memory over NVLink from inside the solve "
                          "kernel (one launch per GPU); rounds = NCCL send/recv + all-reduce per band")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="c4: skip the C2 / C5 lines under extra")
     args = ap.parse_args()
-    # defaults that finish within minutes: steps take 3.5 ms (c2), ~0.1 s (c1), seconds (c4, c3, c5)
+    # defaults that finish within minutes: a C4 step is seconds (65 536 queries), c2 3.5 ms, c1 ~0.1 s, c3 / c5 seconds
     if args.steps is None:
         args.steps = {"c2": 30, "c1": 30}.get(args.workload, 2) if args.impl == "ours" else 2
     if args.warmup is None:

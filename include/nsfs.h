@@ -22,6 +22,7 @@
 #ifndef NSFS_H
 #define NSFS_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -110,6 +111,12 @@ int nsfs_check_trajectory(nsfs_t* h, int n, const int32_t* ij, int t_id, int* sa
 int nsfs_plan(nsfs_t* h, int algo, int cost_mode, int si, int sj, int gi, int gj,
               int32_t* path_ij, int cap, int* n_path, double* g_goal, nsfs_stats* st);
 
+/* The path of the last nsfs_plan call on this handle once more, without searching again: for a caller whose buffer was too
+ * small (NSFS_E_TRUNC told it the length).  replaces: nothing upstream (plan() returns a std::vector of whatever length,
+ * astar.cpp:70-85); it spares the drop-in children a second search.  NSFS_E_NOFIELD when the search state is gone (another
+ * search or a map change came in between): plan again. */
+int nsfs_last_path(nsfs_t* h, int32_t* path_ij, int cap, int* n_path);
+
 /* ---- batched queries -----------------------------------------------------------------------------
  * nq independent plan() calls on the current map; sg4[4q..] = {si, sj, gi, gj}.
  * Per query: status (NSFS_OK / NSFS_E_RANGE / NSFS_E_HEAP), g_goal, path_len (cells), settled (expansions).
@@ -195,6 +202,12 @@ int nsfs_los_batch(nsfs_t* h, int n, const int32_t* seg4, int8_t* out);
 /* replaces: the isLos loop of makeAnyAnglePath (core.cpp:537-558) over turning points already converted
  * with pos2idx.  keep[t] = 1 if point t survives (first and last always do). */
 int nsfs_any_angle(nsfs_t* h, int n, const int32_t* pts_ij, uint8_t* keep);
+
+/* Page-lock / release a caller-owned host range (cudaHostRegister) so that nsfs_set_map on it is a DMA at PCIe speed instead of a
+ * staged pageable copy.  replaces: nothing upstream; serves MapData's two std::vector<int> planes, which the ROS callbacks
+ * overwrite in place (global_planner.cpp:65-73).  Optional: every host-pointer call works on pageable memory too. */
+int nsfs_pin_host(nsfs_t* h, const void* p, size_t bytes);
+int nsfs_unpin_host(nsfs_t* h, const void* p);
 
 /* ---- service -------------------------------------------------------------------------------------*/
 int         nsfs_sync(nsfs_t* h);

@@ -382,12 +382,14 @@ int nsfs_plan(nsfs_t* h, int algo, int cost_mode, int si, int sj, int gi, int gj
     int rc = enter(h, true);
     if (rc != NSFS_OK) return rc;
     if (si < 0 || si >= h->H || sj < 0 || sj >= h->W || cap < 0) return NSFS_E_ARG;
+    h->last_plan_kind = 0;
     if (algo == NSFS_DJIKSTRA_FIELD) {
         nsfs_stats fs;
         rc = nsfs_field_device(h, si, sj, nullptr, nullptr, &fs);
         if (rc != NSFS_OK) return rc;
         int n = 0; double cost = 0;
         rc = nsfs_field_path(h, gi, gj, path_ij, path_ij ? cap : 0, &n, &cost);
+        h->last_plan_kind = 2; h->last_ks = (long long)gi; h->last_kg = (long long)gj;     // kind 2 keeps the goal as (i, j)
         if (n_path) *n_path = n;
         if (g_goal) *g_goal = cost;
         if (st) { *st = fs; st->launches += 1; }
@@ -403,7 +405,49 @@ int nsfs_plan(nsfs_t* h, int algo, int cost_mode, int si, int sj, int gi, int gj
     if (rc != NSFS_OK) return rc;
     if (n_path) *n_path = len;
     if (status != NSFS_OK) return status;
+    if (len > 1 && h->search.cells && h->search.slots >= 1 && gi >= 0 && gi < h->H && gj >= 0 && gj < h->W) {
+        // the wide kernel ran this query in slot 0 and its parent store is still there: nsfs_last_path can walk it again
+        h->last_plan_kind = 1; h->last_ks = (long long)si * h->W + sj; h->last_kg = (long long)gi * h->W + gj;
+    }
     if (path_ij && len > cap) return NSFS_E_TRUNC;
+    return NSFS_OK;
+}
+
+int nsfs_last_path(nsfs_t* h, int32_t* path_ij, int cap, int* n_path) {
+    int rc = enter(h, true);
+    if (rc != NSFS_OK) return rc;
+    if (!path_ij || cap <= 0) return NSFS_E_ARG;
+    if (h->last_plan_kind == 2) return nsfs_field_path(h, (int)h->last_ks, (int)h->last_kg, path_ij, cap, n_path, nullptr);
+    if (h->last_plan_kind != 1) return NSFS_E_NOFIELD;
+    long long dcap = cap;
+    if (dcap > h->N + 1) dcap = h->N + 1;
+    const size_t o_path = 256;
+    if ((rc = ensure_scratch(h, o_path + (size_t)dcap * 8 + 256)) != NSFS_OK) return rc;
+    char* d = (char*)h->d_scratch;
+    if ((rc = launch_path_walk(h, h->last_ks, h->last_kg, (int32_t*)(d + o_path), (int)dcap, (int*)d)) != NSFS_OK) return rc;
+    int n = 0;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(&n, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n_path) *n_path = n;
+    const long long ncopy = n < dcap ? n : dcap;
+    NSFS_CUDA_TRY(h, cudaMemcpyAsync(path_ij, d + o_path, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return n > cap ? NSFS_E_TRUNC : NSFS_OK;
+}
+
+int nsfs_pin_host(nsfs_t* h, const void* p, size_t bytes) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!p || !bytes) return NSFS_E_ARG;
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) return set_cuda_error(h, cudaGetLastError(), "cudaHostRegister");
+    return NSFS_OK;
+}
+
+int nsfs_unpin_host(nsfs_t* h, const void* p) {
+    int rc = enter(h, false);
+    if (rc != NSFS_OK) return rc;
+    if (!p) return NSFS_E_ARG;
+    if (cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) return set_cuda_error(h, cudaGetLastError(), "cudaHostUnregister");
     return NSFS_OK;
 }
 

@@ -68,6 +68,9 @@ __device__ __forceinline__ unsigned long long window64(const uint32_t* __restric
 }
 
 // Fast path: words [w_lo, w_hi) of the target plane, all of whose cells lie in rows 2 .. H-2.
+// NP = number of bit-sliced counter planes: a count can reach the number of cells of the mask, so 6 planes serve masks of up to
+// 63 cells (the reference's radius-4 disc has 49) and 10 planes every mask build_mask accepts (radius 15: 709 cells).
+template <int NP>
 __global__ void __launch_bounds__(256) inflate_words_kernel(const uint32_t* __restrict__ occ, long long n_words, int W, int R,
                                                             const int* __restrict__ bmax, long long w_lo, long long w_hi,
                                                             int32_t* __restrict__ infl) {
@@ -75,7 +78,9 @@ __global__ void __launch_bounds__(256) inflate_words_kernel(const uint32_t* __re
     const long long wbase = w_lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane);   // first word of this warp
     if (wbase >= w_hi) return;
     const long long w = wbase + lane;
-    uint32_t pl[6] = {0u, 0u, 0u, 0u, 0u, 0u};                  // bit-sliced counters: cell c of my word holds sum_p ((pl[p] >> c) & 1) << p
+    uint32_t pl[NP];                                            // bit-sliced counters: cell c of my word holds sum_p ((pl[p] >> c) & 1) << p
+#pragma unroll
+    for (int p = 0; p < NP; ++p) pl[p] = 0u;
     if (w < w_hi) {
         const long long k0 = w * 32;
         for (int a = -R; a <= R; ++a) {
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(256) inflate_words_kernel(const uint32_t* __re
             for (int t = 0; t <= 2 * bm; ++t) {
                 uint32_t carry = (uint32_t)(win >> t);
 #pragma unroll
-                for (int p = 0; p < 6; ++p) { const uint32_t nc = pl[p] & carry; pl[p] ^= carry; carry = nc; }
+                for (int p = 0; p < NP; ++p) { const uint32_t nc = pl[p] & carry; pl[p] ^= carry; carry = nc; }
             }
         }
     }
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(256) inflate_words_kernel(const uint32_t* __re
     for (int s2 = 0; s2 < 32; ++s2) {
         int v = 0;
 #pragma unroll
-        for (int p = 0; p < 6; ++p) v |= (int)((__shfl_sync(0xffffffffu, pl[p], s2) >> lane) & 1u) << p;
+        for (int p = 0; p < NP; ++p) v |= (int)((__shfl_sync(0xffffffffu, pl[p], s2) >> lane) & 1u) << p;
         if (wbase + s2 < w_hi) infl[(wbase + s2) * 32 + lane] = v;
     }
 }
@@ -167,8 +172,13 @@ int launch_inflate(nsfs_planner* h, const int32_t* d_lo, int occ_thresh, double 
     long long w_lo = (2ll * h->W + 31) / 32, w_hi = ((long long)(h->H - 1) * h->W) / 32;
     if (w_hi < w_lo) w_hi = w_lo;
     const long long fast_lo = w_lo * 32, fast_hi = w_hi * 32;
-    if (w_hi > w_lo)
-        inflate_words_kernel<<<(unsigned)((w_hi - w_lo + 255) / 256), 256, 0, h->stream>>>(d_occ_scratch, n_words, h->W, mk.R, d_bmax, w_lo, w_hi, d_infl);
+    int mask_cells = 0;
+    for (int t = 0; t < 31; ++t) if (mk.bmax[t] >= 0) mask_cells += 2 * mk.bmax[t] + 1;
+    if (w_hi > w_lo) {
+        const unsigned blocks = (unsigned)((w_hi - w_lo + 255) / 256);
+        if (mask_cells <= 63) inflate_words_kernel<6><<<blocks, 256, 0, h->stream>>>(d_occ_scratch, n_words, h->W, mk.R, d_bmax, w_lo, w_hi, d_infl);
+        else inflate_words_kernel<10><<<blocks, 256, 0, h->stream>>>(d_occ_scratch, n_words, h->W, mk.R, d_bmax, w_lo, w_hi, d_infl);
+    }
     // everything else, with the guards spelled out: rows 0 .. row_a and row_b .. H (row H = the keys past the grids)
     int row_a = (int)((fast_lo + h->W - 1) / h->W), row_b = (int)(fast_hi / h->W);
     if (w_hi == w_lo || row_a >= row_b) { row_a = h->H; row_b = h->H + 1; }     // no fast range: all rows 0 .. H in one list

@@ -153,6 +153,9 @@ struct nsfs_planner {
     void* h_pinned = nullptr;  size_t pinned_bytes = 0;
 
     long long launches = 0;
+    // what nsfs_last_path can walk again: 0 nothing, 1 the parent store of slot 0 of the wide kernel (last nsfs_plan), 2 the predecessor field
+    int last_plan_kind = 0;
+    long long last_ks = 0, last_kg = 0;
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
@@ -219,6 +222,7 @@ int launch_inflate(nsfs_planner* h, const int32_t* d_lo, int occ_thresh, double 
 int launch_fallback_small(nsfs_planner* h, int nq, const int32_t* d_q, int32_t* d_status, long long* d_settled, int32_t* d_cells,
                           long long* d_stats5);
 
+int launch_path_walk(nsfs_planner* h, long long ks, long long kg, int32_t* d_path, int cap, int* d_n);
 int launch_los_batch(nsfs_planner* h, int n, const int32_t* d_seg4, int8_t* d_out);
 int launch_any_angle(nsfs_planner* h, int n, const int32_t* d_pts, uint8_t* d_keep);
 

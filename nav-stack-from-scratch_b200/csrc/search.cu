@@ -573,6 +573,31 @@ void search_free(nsfs_planner* h) {
     SearchWork& s = h->search;
     cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter);
     s = SearchWork();
+    if (h->last_plan_kind == 1) h->last_plan_kind = 0;      // the parent store nsfs_last_path would walk is gone
+}
+
+// The back-track of the last single query again (astar.cpp:70-82), for a caller whose path buffer was too small: the parent
+// store of slot 0 still holds that search.  One thread chases the chain.
+__global__ void path_walk_kernel(const uint4* __restrict__ cells, int W, long long N, uint32_t ks, uint32_t kg, int32_t* __restrict__ out,
+                                 int cap, int* __restrict__ n_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t k = kg;
+    int plen = 0;
+    for (;;) {
+        if (plen < cap) { out[2 * plen] = (int)(k / (uint32_t)W); out[2 * plen + 1] = (int)(k % (uint32_t)W); }
+        plen++;
+        if (k == ks || (long long)plen > N) break;
+        k = __ldcg(cells + k).z;
+    }
+    *n_out = plen;
+}
+
+int launch_path_walk(nsfs_planner* h, long long ks, long long kg, int32_t* d_path, int cap, int* d_n) {
+    if (!h->search.cells) return NSFS_E_NOFIELD;
+    path_walk_kernel<<<1, 1, 0, h->stream>>>(h->search.cells, h->W, h->N, (uint32_t)ks, (uint32_t)kg, d_path, cap, d_n);
+    h->launches++;
+    NSFS_CUDA_TRY(h, cudaGetLastError());
+    return NSFS_OK;
 }
 
 // find_better_point on the shared-memory kernel: no per-query HBM state at all.

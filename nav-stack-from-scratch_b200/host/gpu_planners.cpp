@@ -34,6 +34,8 @@ GpuPlannerBase::GpuPlannerBase(std::string cost_mode, MapData& map_data) : GridP
 }
 
 GpuPlannerBase::~GpuPlannerBase() {
+    for (int k = 0; k < 2; ++k)
+        if (pinned_[k] && handle_) nsfs_unpin_host(handle_, pinned_[k]);
     if (handle_) nsfs_destroy(handle_);
     handle_ = nullptr;
 }
@@ -44,7 +46,11 @@ void GpuPlannerBase::prepPlanner(std::string cost_mode, MapData& map_data) {
     map_width_ = map_data.map_size_.j;
     cell_size_ = map_data.cell_size_;
     map_origin_.setCoords(map_data.origin_.x, map_data.origin_.y);
-    if (handle_) { nsfs_destroy(handle_); handle_ = nullptr; }
+    if (handle_) {
+        for (int k = 0; k < 2; ++k) { if (pinned_[k]) nsfs_unpin_host(handle_, pinned_[k]); pinned_[k] = nullptr; pinned_bytes_[k] = 0; }
+        nsfs_destroy(handle_);
+        handle_ = nullptr;
+    }
     dirty_ = true;
     ensureHandle(map_data);
 }
@@ -86,6 +92,17 @@ void GpuPlannerBase::uploadMap(MapData& map_data) {
     if (map_data.grid_inflation_.size() < n || map_data.grid_logodds_.size() < n)
         throw std::out_of_range("MapData grids are smaller than map_size_");       // what .at() would report
     static_assert(sizeof(int) == sizeof(int32_t), "MapData stores int planes");
+    if (sync_ == MapSync::EveryCallPinned) {
+        // page-lock the caller's vectors once; re-register only when a vector was reallocated (pointer or size changed)
+        const void* ptr[2] = {map_data.grid_inflation_.data(), map_data.grid_logodds_.data()};
+        for (int k = 0; k < 2; ++k) {
+            if (pinned_[k] == ptr[k] && pinned_bytes_[k] == n * sizeof(int)) continue;
+            if (pinned_[k]) nsfs_unpin_host(handle_, pinned_[k]);
+            pinned_[k] = nullptr; pinned_bytes_[k] = 0;
+            if (nsfs_pin_host(handle_, ptr[k], n * sizeof(int)) == NSFS_OK) { pinned_[k] = ptr[k]; pinned_bytes_[k] = n * sizeof(int); }
+            // a failed registration (e.g. the range is already registered by the caller) is not an error: the copy just stays pageable
+        }
+    }
     const int rc = nsfs_set_map(handle_, reinterpret_cast<const int32_t*>(map_data.grid_inflation_.data()),
                                 reinterpret_cast<const int32_t*>(map_data.grid_logodds_.data()), map_data.lo_thresh_);
     if (rc != NSFS_OK) fail(rc, "nsfs_set_map");
@@ -161,9 +178,15 @@ std::vector<Pos2D> GpuPlannerBase::runPlan(int algo, Index s, Index g, MapData& 
     double g_goal = 0.0;
     int rc = nsfs_plan(handle_, algo, modeCode(cost_mode_), s.i, s.j, g.i, g.j, path_buf_.data(), (int)(path_buf_.size() / 2), &n,
                        &g_goal, &stats_);
-    if (rc == NSFS_E_TRUNC) {              // path longer than the buffer: now its exact length is known
+    if (rc == NSFS_E_TRUNC) {              // path longer than the buffer: its exact length is known now; fetch it without searching again
         path_buf_.resize(2 * (size_t)n);
-        rc = nsfs_plan(handle_, algo, modeCode(cost_mode_), s.i, s.j, g.i, g.j, path_buf_.data(), n, &n, &g_goal, &stats_);
+        int n2 = 0;
+        rc = nsfs_last_path(handle_, path_buf_.data(), n, &n2);
+        if (rc == NSFS_OK && n2 == n) {
+            // the parent store (or predecessor field) of the search that just ran was walked again: same path, whole this time
+        } else {
+            rc = nsfs_plan(handle_, algo, modeCode(cost_mode_), s.i, s.j, g.i, g.j, path_buf_.data(), n, &n, &g_goal, &stats_);
+        }
     }
     if (rc != NSFS_OK) fail(rc, "nsfs_plan");
     last_g_goal_ = g_goal;
@@ -171,6 +194,19 @@ std::vector<Pos2D> GpuPlannerBase::runPlan(int algo, Index s, Index g, MapData& 
     path_world.reserve((size_t)n);
     for (int t = 0; t < n; ++t) path_world.push_back(toPos(path_buf_[2 * t], path_buf_[2 * t + 1]));
     return path_world;
+}
+
+BatchPlan GpuPlannerBase::planBatch(const std::vector<int32_t>& sg4, MapData& map_data) {
+    uploadMap(map_data);
+    const int nq = (int)(sg4.size() / 4);
+    BatchPlan out;
+    out.status.assign((size_t)nq, 0); out.path_len.assign((size_t)nq, 0); out.g_goal.assign((size_t)nq, 0.0); out.settled.assign((size_t)nq, 0);
+    if (!nq) return out;
+    const int rc = nsfs_plan_batch(handle_, algoCode(), modeCode(cost_mode_), nq, sg4.data(), out.status.data(), out.g_goal.data(),
+                                   out.path_len.data(), out.settled.data(), nullptr, 0, &out.stats);
+    if (rc != NSFS_OK) fail(rc, "nsfs_plan_batch");
+    stats_ = out.stats;
+    return out;
 }
 
 // ---- children ---------------------------------------------------------------------------------------------
@@ -380,6 +416,39 @@ int nsfsh_set_map(void* p, const int32_t* infl, const int32_t* lo) {
     s->map.grid_inflation_.assign(infl, infl + n);      // what the ROS callbacks do (global_planner.cpp:65-73)
     s->map.grid_logodds_.assign(lo, lo + n);
     return 0;
+}
+
+// 0 = EveryCall (pageable copy of the caller's vectors on every plan: the reference's contract), 1 = OnNotify, 2 = EveryCallPinned
+int nsfsh_set_map_sync(void* p, int mode) {
+    auto* s = static_cast<Session*>(p);
+    const nsfs_host::MapSync m = mode == 1 ? nsfs_host::MapSync::OnNotify : (mode == 2 ? nsfs_host::MapSync::EveryCallPinned : nsfs_host::MapSync::EveryCall);
+    if (auto* g = dynamic_cast<nsfs_host::GpuPlannerBase*>(s->main_planner.get())) g->setMapSync(m);
+    s->fallback->setMapSync(m);
+    return 0;
+}
+
+int nsfsh_notify_map_changed(void* p) {
+    auto* s = static_cast<Session*>(p);
+    if (auto* g = dynamic_cast<nsfs_host::GpuPlannerBase*>(s->main_planner.get())) g->notifyMapChanged();
+    s->fallback->notifyMapChanged();
+    return 0;
+}
+
+// nq plan(Index, Index) calls of the session's main planner on one upload of its MapData (BASELINE config C4)
+int nsfsh_plan_batch_idx(void* p, int nq, const int32_t* sg4, int32_t* status, double* g_goal, int32_t* path_len, long long* settled,
+                         double* gpu_ms) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        auto* g = dynamic_cast<nsfs_host::GpuPlannerBase*>(s->main_planner.get());
+        if (!g) return 2;
+        const std::vector<int32_t> q(sg4, sg4 + 4 * (size_t)nq);
+        const nsfs_host::BatchPlan r = g->planBatch(q, s->map);
+        memcpy(status, r.status.data(), (size_t)nq * 4); memcpy(path_len, r.path_len.data(), (size_t)nq * 4);
+        memcpy(g_goal, r.g_goal.data(), (size_t)nq * 8); memcpy(settled, r.settled.data(), (size_t)nq * 8);
+        if (gpu_ms) *gpu_ms = r.stats.gpu_ms;
+        return 0;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
 }
 
 static int emit(const std::vector<bot_utils::Pos2D>& path, double* out_xy, int cap, int* n) {

@@ -24,7 +24,21 @@ namespace nsfs_host {
 
 // When does the planner re-upload MapData?  The reference reads the caller's vectors afresh on every call
 // (global_planner.cpp:65-73 replaces them whenever a ROS message arrives), so EveryCall is the default.
-enum class MapSync { EveryCall, OnNotify };
+// EveryCallPinned: same contract as EveryCall, but the caller's two vectors are page-locked once (cudaHostRegister through
+// nsfs_pin_host) and stay registered while their data pointers and sizes do not change (the ROS callbacks copy-assign into
+// the same vectors, global_planner.cpp:65-73, so they do not), which makes the per-call upload a DMA at PCIe speed.
+enum class MapSync { EveryCall, OnNotify, EveryCallPinned };
+
+// Results of a batch of plan() calls on one map (no reference counterpart: GlobalPlanner plans one request at a time;
+// the batch is what BASELINE.json's config "batched 65,536 Astar start/goal queries" runs).  Same per-query values as
+// plan(): status (NSFS_OK / NSFS_E_RANGE where plan() would throw std::out_of_range), nodes[goal].g, raw path length in
+// cells (1 = no path, astar.cpp:129-135), settled cells.
+struct BatchPlan {
+    std::vector<int32_t> status, path_len;
+    std::vector<double> g_goal;
+    std::vector<long long> settled;
+    nsfs_stats stats{};
+};
 
 class GpuPlannerBase : public GridPlannerCore {
 public:
@@ -37,6 +51,8 @@ public:
     // Opt-in: search the textbook 8-connected grid (rows and columns bounds-checked, diagonal steps
     // sqrt(2)) instead of the reference's quirk graph.  Default false = reference behaviour.
     void setTextbookGraph(bool on);
+    // nq independent plan(Index, Index, map) calls of this child on one upload of the map (sg4 = {si, sj, gi, gj} per query)
+    BatchPlan planBatch(const std::vector<int32_t>& sg4, bot_utils::MapData& map_data);
     const nsfs_stats& lastStats() const { return stats_; }
     double lastGoalCost() const { return last_g_goal_; }   // nodes[goal].g of the last plan (1e5 = unreachable)
     // The path consumer's check of a trajectory against the current map: Commander::checkTrajectorySafety
@@ -58,6 +74,7 @@ protected:
     void ensureHandle(bot_utils::MapData& map_data);
     void uploadMap(bot_utils::MapData& map_data);
     std::vector<bot_utils::Pos2D> runPlan(int algo, bot_utils::Index s, bot_utils::Index g, bot_utils::MapData& map_data);
+    virtual int algoCode() const = 0;
     static int modeCode(const std::string& cost_mode);
     [[noreturn]] void fail(int code, const char* where) const;
 
@@ -69,6 +86,8 @@ protected:
     nsfs_stats stats_{};
     double last_g_goal_ = 0.0;
     std::vector<int32_t> path_buf_;
+    const void* pinned_[2] = {nullptr, nullptr};     // EveryCallPinned: the registered vectors' data pointers
+    size_t pinned_bytes_[2] = {0, 0};
 #ifdef NSFS_USE_REFERENCE_HEADERS
     // the reference base class already owns map_height_, map_width_, cell_size_, map_origin_, cost_mode_
 #endif
@@ -79,6 +98,7 @@ public:
     GpuAstar() = default;
     GpuAstar(std::string cost_mode, bot_utils::MapData& map_data) : GpuPlannerBase(std::move(cost_mode), map_data) {}
 protected:
+    int algoCode() const override { return NSFS_ASTAR; }
     std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
     std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
 };
@@ -97,6 +117,7 @@ public:
     bot_utils::Pos2D find_better_point(bot_utils::Index idx_bad, bot_utils::MapData& map_data);
     bot_utils::Pos2D find_better_point(bot_utils::Pos2D pos_bad, bot_utils::MapData& map_data);
 protected:
+    int algoCode() const override { return NSFS_DJIKSTRA; }
     std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
     std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
 private:
@@ -111,6 +132,7 @@ public:
     GpuThetaStar() = default;
     GpuThetaStar(std::string cost_mode, bot_utils::MapData& map_data) : GpuPlannerBase(std::move(cost_mode), map_data) {}
 protected:
+    int algoCode() const override { return NSFS_THETASTAR; }
     std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
     std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
 };

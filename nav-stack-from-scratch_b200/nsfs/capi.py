@@ -67,6 +67,9 @@ def lib():
         L.nsfs_test_pos_batch.argtypes = [vp, i32, vp, vp]
         L.nsfs_check_trajectory.argtypes = [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         L.nsfs_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(dbl), C.POINTER(Stats)]
+        L.nsfs_last_path.argtypes = [vp, vp, i32, C.POINTER(i32)]
+        L.nsfs_pin_host.argtypes = [vp, vp, C.c_size_t]
+        L.nsfs_unpin_host.argtypes = [vp, vp]
         L.nsfs_plan_batch.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_plan_batch_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_field.argtypes = [vp, i32, i32, vp, vp, C.POINTER(Stats)]
@@ -209,6 +212,14 @@ class Planner:
         if want_path:
             out["path"] = path[: min(n.value, cap)].copy()
         return out
+
+    def last_path(self, cap):
+        """The path of the last plan() again without searching (status E_NOFIELD when the search state is gone)."""
+        path = np.zeros((int(cap), 2), np.int32)
+        n = C.c_int(0)
+        rc = self.L.nsfs_last_path(self.h, _ptr(path), int(cap), C.byref(n))
+        self._check(rc, allow=(E_TRUNC, E_NOFIELD))
+        return dict(status=rc, path=path[: min(n.value, int(cap))].copy(), n_path=n.value)
 
     def plan_batch(self, algo, mode, sg4, path_cap=0):
         sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)

@@ -19,7 +19,8 @@ HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
 
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
-           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory", "nsfsh_set_graph")
+           "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory", "nsfsh_set_graph", "nsfsh_set_map_sync",
+           "nsfsh_notify_map_changed", "nsfsh_plan_batch_idx")
 
 _libs = {}
 
@@ -48,6 +49,9 @@ def lib(so_path=None):
         L.nsfsh_plan_request.argtypes = [vp, dbl, dbl, dbl, dbl, vp, i32, C.POINTER(i32), vp, vp, vp]
         L.nsfsh_set_graph.argtypes = [vp, i32]
         L.nsfsh_check_trajectory.argtypes = [vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.nsfsh_set_map_sync.argtypes = [vp, i32]
+        L.nsfsh_notify_map_changed.argtypes = [vp]
+        L.nsfsh_plan_batch_idx.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(dbl)]
         _libs[path] = L
     return _libs[path]
 
@@ -110,6 +114,27 @@ class Session:
         infl = np.ascontiguousarray(infl, np.int32)
         lo = np.ascontiguousarray(lo, np.int32)
         self.L.nsfsh_set_map(self.s, infl.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p))
+
+    def set_map_sync(self, mode):
+        """'every_call' (pageable upload per plan: the reference's contract, default) | 'on_notify' | 'every_call_pinned'."""
+        self.L.nsfsh_set_map_sync(self.s, {"every_call": 0, "on_notify": 1, "every_call_pinned": 2}[mode])
+
+    def notify_map_changed(self):
+        self.L.nsfsh_notify_map_changed(self.s)
+
+    def plan_batch_idx(self, sg4):
+        """nq plan(Index, Index) calls of the main planner on one upload of the session's MapData (GpuPlannerBase::planBatch)."""
+        sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)
+        nq = len(sg4)
+        status, plen = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        g, settled = np.zeros(nq, np.float64), np.zeros(nq, np.int64)
+        ms = C.c_double(0)
+        vp = C.c_void_p
+        rc = self.L.nsfsh_plan_batch_idx(self.s, nq, sg4.ctypes.data_as(vp), status.ctypes.data_as(vp), g.ctypes.data_as(vp),
+                                         plen.ctypes.data_as(vp), settled.ctypes.data_as(vp), C.byref(ms))
+        if rc != 0:
+            raise PlannerError(self.L.nsfsh_error(self.s).decode())
+        return dict(status=status, g_goal=g, path_len=plen, settled=settled, gpu_ms=ms.value)
 
     def _path(self, fn, *args):
         cap = 4 * (self.H + self.W) + 64

@@ -308,6 +308,23 @@ def _tensor_from_ptr(torch, ptr, shape, typestr, device):
     return torch.as_tensor(raw, device=device)
 
 
+def field_checksum(torch, g_rows, pred_rows, key0):
+    """Position-weighted sums mod 2^64 of the fp32 bit patterns of g and of (pred + 1) over the global keys key0, key0 + 1, ...
+    (torch CUDA tensors).  The sums of disjoint row blocks add up (mod 2^64) to the whole field's, so N shards can be checked
+    against the single-GPU field without gathering it; integer arithmetic wraps, so the order of summation is irrelevant.
+    Returns two Python ints."""
+    n = g_rows.numel()
+    gi = g_rows.reshape(-1).view(torch.int32)
+    pr = pred_rows.reshape(-1)
+    sg, sp, chunk = 0, 0, 1 << 25
+    for o in range(0, n, chunk):
+        e = min(o + chunk, n)
+        w = torch.arange(key0 + o, key0 + e, device=gi.device, dtype=torch.int64) * 2 + 1
+        sg += int((gi[o:e].to(torch.int64) * w).sum().item())
+        sp += int(((pr[o:e].to(torch.int64) + 1) * w).sum().item())
+    return sg % (1 << 64), sp % (1 << 64)
+
+
 def make_gpu_shard(part: RowPartition, rank: int, infl, lo, device=0, lo_thresh=10):
     """Slice the held rows out of global int32 planes (numpy [H, W]) and build the shard."""
     a, b = part.held(rank)

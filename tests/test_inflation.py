@@ -70,10 +70,13 @@ def test_gpu_inflation_matches_the_reference_planes(gpu_lib, gocc, case):
 @pytest.mark.gpu
 def test_gpu_inflation_random_planes_edges_and_exception(gpu_lib, oracle_mod, gocc):
     rng = np.random.RandomState(12)
-    for (H, W, dens, radius) in ((97, 131, 0.03, 0.2), (64, 64, 0.2, 0.2), (200, 90, 0.01, 0.35), (70, 300, 0.05, 0.1)):
+    # the last three: discs of 149 / 709 cells in dense planes, so counts pass 63, 127, ... (a 6-plane counter would wrap there)
+    for (H, W, dens, radius) in ((97, 131, 0.03, 0.2), (64, 64, 0.2, 0.2), (200, 90, 0.01, 0.35), (70, 300, 0.05, 0.1),
+                                 (120, 150, 0.6, 0.35), (90, 200, 0.95, 0.35), (100, 128, 0.5, 0.75)):
         lo = np.where(rng.rand(H, W) < dens, 15, rng.randint(-20, 10, (H, W))).astype(np.int32)
-        lo[H - 1, W - 8:] = 0                                        # keep clear of the throwing corner ...
-        lo[H - 9:, W - 8:] = np.minimum(lo[H - 9:, W - 8:], 0)
+        R = max(int(round(radius / 0.05)), 7)
+        lo[H - 1, W - R - 1:] = 0                                    # keep clear of the throwing corner ...
+        lo[H - R - 2:, W - R - 1:] = np.minimum(lo[H - R - 2:, W - R - 1:], 0)
         rc, want = oracle_mod.occ_inflation(lo, 10, radius, 0.05)
         P = gpu_lib.Planner(H, W)
         assert P.set_map_logodds(lo, 10, 10, radius, 0.05) == rc == 0
