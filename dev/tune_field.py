@@ -1,40 +1,34 @@
+"""Sweep the field solver's scheduling knobs on one map (same bits expected everywhere).
+    python dev/tune_field.py [size]     env: MODES=0,1,2 TILES=0 DELTAS=128 INNERS=16 IDLES=1000 WAITS=200 SCHED=0 MERGE=0 FENCE=0 GATES=0"""
 import sys, os, itertools
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'nav-stack-from-scratch_b200'))
 import numpy as np
 from nsfs import mapgen, capi
 H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-infl, lo = mapgen.synth_map(H, W, 0.10, 5)
+seed = 11 if H == 16384 else 5
+infl, lo = mapgen.synth_map_rows(H, W, 0.10, seed, 0, H)
 P = capi.Planner(H, W); P.set_map(infl, lo)
-src = mapgen.field_source(infl, lo)
+fm = mapgen.free_mask(infl[H // 2:H // 2 + 1], lo[H // 2:H // 2 + 1])[0]
+sj = W // 2
+while not fm[sj]: sj += 1
+src = (H // 2, sj)
+ev = lambda k, d: [int(x) for x in os.environ.get(k, d).split(',')]
 ref = None
-P.set_option('field_mode', int(os.environ.get('MODE', '0')))
-inners = [int(x) for x in os.environ.get('INNERS', '1,2,4,8').split(',')]
-deltas = [float(x) for x in os.environ.get('DELTAS', '16,32,64,128,1000000').split(',')]
-idles = [int(x) for x in os.environ.get('IDLES', '100').split(',')]
-alphas = [int(x) for x in os.environ.get('ALPHAS', '100').split(',')]
-dins = [int(x) for x in os.environ.get('DINS', '12').split(',')]
-groups = [int(x) for x in os.environ.get('TGROUPS', '0').split(',')]
-gates = [int(x) for x in os.environ.get('GATES', '0').split(',')]
-earlies = [int(x) for x in os.environ.get('EARLY', '0').split(',')]   # 0/1 on, 2 off
-merges = [int(x) for x in os.environ.get('MERGE', '0').split(',')]    # 0/1 on, 2 off
-fences = [int(x) for x in os.environ.get('FENCE', '0').split(',')]    # 1: release-atomic key posts
-P.set_option('field_sched_ns', int(os.environ.get('SCHED', '0')))
-waits = [int(x) for x in os.environ.get('WAITS', '200').split(',')]
-for inner, delta, alpha, idle, din, wait in itertools.product(inners, deltas, alphas, idles, dins, waits):
-  for grp, gate, early, merge, fence in itertools.product(groups, gates, earlies, merges, fences):
-    P.set_option('field_groups', grp); P.set_option('field_gate', gate)
-    P.set_option('field_early', early); P.set_option('field_merge', merge); P.set_option('field_fence', fence)
-    P.set_option('field_delta_in', din); P.set_option('field_wait_ns', wait)
-    P.set_option('field_idle_ns', idle)
-    P.set_option('field_alpha', alpha)
-    P.set_option('field_inner', inner); P.set_option('field_delta', int(delta))
+for mode, tiles, delta, inner, idle, wait, merge, fence, gate in itertools.product(ev('MODES', '0,1,2'), ev('TILES', '0'), ev('DELTAS', '128'), ev('INNERS', '16'),
+                                                                           ev('IDLES', '1000'), ev('WAITS', '200'), ev('MERGE', '0'), ev('FENCE', '0'), ev('GATES', '0')):
+    for k, v in (('field_mode', mode), ('field_tiles_per_sm', tiles), ('field_delta', delta), ('field_inner', inner), ('field_idle_ns', idle),
+                 ('field_wait_ns', wait), ('field_merge', merge), ('field_fence', fence), ('field_gate', gate), ('field_sched_ns', int(os.environ.get('SCHED', '0')))):
+        P.set_option(k, v)
     best = None
     for _ in range(4):
         r = P.field_device(src)
         st = r['stats']
-        if best is None or st['gpu_ms'] < best['gpu_ms']: best = st
-    g = P.field(src)['g']
-    if ref is None: ref = g
-    same = np.array_equal(ref, g)
-    print(f"early {early} merge {merge} fence {fence} gate {gate} groups {grp} din {din} wait {wait} idle {idle} alpha {alpha} inner {inner} delta {delta:9.0f}: gpu_ms {best['gpu_ms']:.3f} solve_ms {best['main_kernel_ms']:.3f} rounds {best['rounds']} visits {best['tile_visits']} sweeps {best['pops']} reached {r['reached']} same_bits {same}", flush=True)
+        if best is None or st['main_kernel_ms'] < best['main_kernel_ms']: best = st
+    import torch
+    from nsfs import sharded_field as sf
+    g = sf._tensor_from_ptr(torch, r['d_g'], (H, W), '<f4', torch.device('cuda', 0))
+    chk = sf.field_checksum(torch, g, sf._tensor_from_ptr(torch, r['d_pred'], (H, W), '|u1', torch.device('cuda', 0)), 0)
+    if ref is None: ref = chk
+    print(f"mode {mode} tiles/sm {tiles} delta {delta} inner {inner} idle {idle} wait {wait} merge {merge} fence {fence} gate {gate}: solve_ms {best['main_kernel_ms']:.3f} "
+          f"gpu_ms {best['gpu_ms']:.3f} visits {best['tile_visits']} reached {r['reached']} same_bits {chk == ref}", flush=True)

@@ -153,7 +153,9 @@ int nsfs_field_path(nsfs_t* h, int gi, int gj, int32_t* path_ij, int cap, int* n
  *   nsfs_field_finish(h, st)               predecessor field + reached count of the counted rows; then nsfs_field_device*
  * All three leave results on the device (nsfs_field_device's pointers stay valid). */
 int nsfs_field_begin(nsfs_t* h, int si, int sj);
-int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, int* n_improved);   /* device values */
+int nsfs_field_inject_rows(nsfs_t* h, int row0, int nrows, const float* d_vals, int* n_improved);   /* device values: rows read from
+                                            another shard's plane (nsfs_field_pointers) DURING its solve, i.e. in the plane's working
+                                            representation (32-bit words, Q17.15 fixed point), not fp32 cost units */
 int nsfs_field_relax(nsfs_t* h, nsfs_stats* st);
 /* Same, but nothing is relaxed beyond the cost `cap`: tiles whose smallest pending value exceeds it stay pending.
  * min_pending = the smallest value still pending afterwards (+inf when the shard is at its fixed point).  Lets all
@@ -161,7 +163,8 @@ int nsfs_field_relax(nsfs_t* h, nsfs_stats* st);
 int nsfs_field_relax_until(nsfs_t* h, float cap, float* min_pending, nsfs_stats* st);
 int nsfs_field_min_pending(nsfs_t* h, float* min_pending);   /* e.g. after nsfs_field_inject_rows */
 int nsfs_field_finish(nsfs_t* h, nsfs_stats* st);
-int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred);   /* valid after nsfs_field_begin */
+int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred);   /* valid after nsfs_field_begin; the g plane holds
+                                            Q17.15 words until nsfs_field_finish turns it into fp32 cost units in place */
 
 /* ---- peer-to-peer shards over NVLink (one process per GPU) ----------------------------------------------------
  * Instead of exchange rounds, each shard's solve kernel pushes every improvement of its first / last two owned rows
@@ -186,6 +189,35 @@ int nsfs_field_peer_detach(nsfs_t* h);
 int nsfs_field_pending_count(nsfs_t* h, int* n_pending);
 int nsfs_field_set_counter(nsfs_t* h, int total);
 int nsfs_field_relax_p2p(nsfs_t* h, nsfs_stats* st);
+
+/* ---- groups: one process per GPU, for the two sharded configurations --------------------------------------
+ * replaces: nothing upstream (the reference is single-threaded and single-device); this is the C++/C entry a GlobalPlanner
+ * process per GPU would use instead of looping GridPlannerCore::generatePath over requests (global_planner.cpp:102-130, 183).
+ * NCCL (libnccl.so.2) is bound at run time; without it nsfs_group_unique_id / nsfs_group_create return NSFS_E_CUDA.
+ *   rank 0: nsfs_group_unique_id(id); ship the 128 bytes to the other ranks out of band (a ROS parameter, a file, a socket)
+ *   every rank: nsfs_group_create(&g, id, rank, world, device)
+ * Batched queries (BASELINE config "65,536 Astar queries sharded across 1/2/4/8 B200"):
+ *   nsfs_set_map*(h) on the root only; nsfs_group_broadcast_map(g, h, root) ships the packed bit planes (N/4 bytes);
+ *   nsfs_group_plan_batch(g, h, ...): every rank passes all nq queries and gets all nq results; rank r plans the contiguous
+ *   slice [r*nq/world ..) on its own GPU, results are all-gathered.  No exchange during the search.
+ * Row-block field (BASELINE config "16384x16384 tile-partitioned across 2/4/8 B200 with NVLink halo exchange"):
+ *   each rank's handle covers its owned rows + 4 rows of map per side (see "row-partitioned field" above);
+ *   nsfs_group_field_attach(g, h, held_lo, own_lo, own_hi) once (global row numbers; exchanges the CUDA IPC handles over NCCL);
+ *   nsfs_group_field_solve(g, h, si, sj, &reached, &st) per field (global source): one solve kernel per GPU, boundary rows
+ *   posted peer to peer over NVLink from inside it; then nsfs_field_pointers / nsfs_field_path on the owning shard. */
+typedef struct nsfs_group nsfs_group_t;
+int  nsfs_group_unique_id(unsigned char id[128]);
+int  nsfs_group_create(nsfs_group_t** out, const unsigned char id[128], int rank, int world, int device);
+void nsfs_group_destroy(nsfs_group_t* g);
+int  nsfs_group_rank(const nsfs_group_t* g);
+int  nsfs_group_world(const nsfs_group_t* g);
+int  nsfs_group_barrier(nsfs_group_t* g);
+const char* nsfs_group_error(const nsfs_group_t* g);
+int  nsfs_group_broadcast_map(nsfs_group_t* g, nsfs_t* h, int root);
+int  nsfs_group_plan_batch(nsfs_group_t* g, nsfs_t* h, int algo, int cost_mode, int nq, const int32_t* sg4, int32_t* status,
+                           double* g_goal, int32_t* path_len, long long* settled, nsfs_stats* st);
+int  nsfs_group_field_attach(nsfs_group_t* g, nsfs_t* h, int held_lo, int own_lo, int own_hi);
+int  nsfs_group_field_solve(nsfs_group_t* g, nsfs_t* h, int si, int sj, long long* reached_total, nsfs_stats* st);
 
 /* ---- fallback ------------------------------------------------------------------------------------
  * replaces: Djikstra::find_better_point(Index, MapData&) (djikstra.cpp:165-273) on a planner prepared
@@ -215,10 +247,12 @@ long long   nsfs_kernel_launches(const nsfs_t* h);   /* kernels launched through
 void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the handle */
 /* Options (all have working defaults; 0 = default unless stated):
  *   "graph"          0 the reference's quirk graph | 1 textbook 8-connected grid; rebuilds the edge masks
- *   "field_mode"     0 asynchronous pull solver | 1 bulk-synchronous rounds | 2 dynamic tile claiming | 3 bucket-ordered solver
- *   "field_delta", "field_inner", "field_idle_ns", "field_wait_ns", "field_sched_ns", "field_early", "field_merge",
- *   "field_gate", "field_groups", "field_delta_in", "field_alpha", "field_fence"   scheduling knobs of the field solvers
- *                    (same bits whatever they are set to; profiles/r01_field_solve_ncu.md says what each measured)
+ *   "field_mode"     warps per resident tile of the field solver: 0 = 4 (8 tiles resident per SM) | 1 = 8 (4 tiles) | 2 = 16 (2 tiles)
+ *   "field_tiles_per_sm"  cap on resident tiles per SM (0 = as many as fit)
+ *   "field_delta", "field_inner", "field_idle_ns", "field_wait_ns", "field_sched_ns", "field_merge", "field_fence"
+ *                    scheduling knobs of the field solver (band width in cost units, passes per sub-block turn, back-offs,
+ *                    merged visits 2 = off, release-atomic key posts 1 = on); the field is solved in exact integer arithmetic,
+ *                    so the result is the same bits whatever they are set to
  *   "search_kernel"  0 auto | 1 one query per warp | 2 four queries per warp;   "search_order"  2 = start a batch in input order
  *   "max_slots", "heap_cap", "team_heap_cap"   query slots (in warps) and open-list capacity per slot
  *   "active_row_lo/hi", "count_row_lo/hi"      row windows of a shard (see the row-partitioned field above)

@@ -1,4 +1,5 @@
 // extern "C" surface of libnsfs_gpu.so (include/nsfs.h): argument checks, staging copies, launches, results.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -483,13 +484,14 @@ int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int
     long long s5[5];
     NSFS_CUDA_TRY(h, cudaMemcpy(s5, d_s5, sizeof(s5), cudaMemcpyDeviceToHost));
     fill_stats(st, s5, h->launches - launches0, ms, main_ms);
-    if (team && d_status) {
-        // queries the batch kernel could not finish exactly (open list beyond its slot, 16-bit step counts): re-run each on
-        // the wide kernel with the worst-case capacity, results written into the same device arrays
+    long long worst = 8 * h->N + 16;
+    if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;
+    if (d_status && (team || h->search.heap_cap < worst)) {
+        // queries that could not be finished exactly (open list beyond its slot; on the batch kernel also 16-bit step counts / sort
+        // keys): re-run each on the wide kernel with the worst-case capacity, results written into the same device arrays
+        // (the host-pointer entry point does the same, so both return the same statuses)
         std::vector<int32_t> stat_h(nq);
         NSFS_CUDA_TRY(h, cudaMemcpy(stat_h.data(), d_status, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-        long long worst = 8 * h->N + 16;
-        if (worst > (1ll << 31) - 64) worst = (1ll << 31) - 64;
         bool any = false;
         for (int q = 0; q < nq; ++q) any = any || stat_h[q] == NSFS_E_HEAP;
         if (any) {
@@ -541,9 +543,10 @@ int nsfs_field_device(nsfs_t* h, int si, int sj, const float** d_g, const uint8_
     if (rc != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
-    h->field.begun = true;
-    if (d_g) *d_g = h->field.g;
+    h->field.finished = true;
+    if (d_g) *d_g = reinterpret_cast<const float*>(h->field.g);
     if (d_pred) *d_pred = h->field.pred;
+    h->field.begun = false;                       // finished: the plane holds fp32 cost units now
     if ((rc = field_read_counts(h, st, launches0, ms, tm.main_kernel_ms())) != NSFS_OK) return rc;
     h->field.valid = true;
     return NSFS_OK;
@@ -557,6 +560,7 @@ int nsfs_field_begin(nsfs_t* h, int si, int sj) {
     if ((rc = launch_field_begin(h, si, sj)) != NSFS_OK) return rc;
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->field.begun = true;
+    h->field.finished = false;
     return NSFS_OK;
 }
 
@@ -584,15 +588,11 @@ static int field_read_counts(nsfs_planner* h, nsfs_stats* st, long long launches
     if (st) {
         memset(st, 0, sizeof(*st));
         st->rounds = counts[2]; st->tile_visits = counts[3]; st->expansions = counts[5];
-        st->pops = counts[8]; st->pushes = counts[9]; st->heap_peak = counts[10];   // bucket kernel: steps, merged posts, empty visits
         st->launches = h->launches - launches0; st->gpu_ms = ms; st->main_kernel_ms = main_ms;
     }
-    if (getenv("NSFS_FIELD_DEBUG"))
-        fprintf(stderr, "[field] visits %d steps %d rounds %d merges %d empty %d | cycles/16: stage %d loop %d end %d end-wait %d\n", counts[3], counts[8], counts[14],
-                counts[9], counts[10], counts[11], counts[12], counts[13], counts[15]);
     if (counts[4] & 2) { snprintf(h->cuda_error, sizeof(h->cuda_error), "field_solve_async_kernel: scheduler bail-out"); return NSFS_E_CUDA; }
-    uint32_t kb = (uint32_t)counts[6];                  // smallest key still pending (float bits; +inf bits = none)
-    memcpy(&h->field.min_pending, &kb, sizeof(kb));
+    const uint32_t kb = (uint32_t)counts[6];            // smallest key still pending (Q17.15; kNoKey = none)
+    h->field.min_pending = kb == kNoKey ? INFINITY : (float)((double)kb / (double)kQOne);
     if (counts[4] & 1) return NSFS_E_RANGE; // a reached cell's expansion throws in the reference
     return NSFS_OK;
 }
@@ -721,7 +721,7 @@ int nsfs_field_min_pending(nsfs_t* h, float* min_pending) {
     uint32_t kb = 0;
     NSFS_CUDA_TRY(h, cudaMemcpyAsync(&kb, h->field.counts + 6, sizeof(kb), cudaMemcpyDeviceToHost, h->stream));
     NSFS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    memcpy(&h->field.min_pending, &kb, sizeof(kb));
+    h->field.min_pending = kb == kNoKey ? INFINITY : (float)((double)kb / (double)kQOne);
     if (min_pending) *min_pending = h->field.min_pending;
     return NSFS_OK;
 }
@@ -737,16 +737,18 @@ int nsfs_field_finish(nsfs_t* h, nsfs_stats* st) {
     if ((rc = launch_field_finish(h)) != NSFS_OK) return rc;
     const float ms = tm.stop_sync();
     NSFS_CUDA_TRY(h, cudaGetLastError());
+    h->field.begun = false;                       // the plane is fp32 cost units from here on: begin again before relaxing
     rc = field_read_counts(h, st, launches0, ms, 0.f);
     if (rc == NSFS_OK) h->field.valid = true;
+    h->field.finished = true;
     return rc;
 }
 
 int nsfs_field_pointers(nsfs_t* h, const float** d_g, const uint8_t** d_pred) {
     int rc = enter(h, true);
     if (rc != NSFS_OK) return rc;
-    if (!h->field.begun) return NSFS_E_NOFIELD;
-    if (d_g) *d_g = h->field.g;
+    if (!h->field.begun && !h->field.finished) return NSFS_E_NOFIELD;
+    if (d_g) *d_g = reinterpret_cast<const float*>(h->field.g);
     if (d_pred) *d_pred = h->field.pred;
     return NSFS_OK;
 }
@@ -851,16 +853,13 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "field_inner")) { h->opt_field_inner = value; return NSFS_OK; }
     if (!strcmp(key, "field_delta")) { h->opt_field_delta = value; return NSFS_OK; }
     if (!strcmp(key, "field_mode")) { h->opt_field_mode = value; return NSFS_OK; }
+    if (!strcmp(key, "field_tiles_per_sm")) { h->opt_field_tiles_per_sm = value; return NSFS_OK; }
+    if (!strcmp(key, "field_gate")) { h->opt_field_gate = value; return NSFS_OK; }
     if (!strcmp(key, "field_idle_ns")) { h->opt_field_idle_ns = value; return NSFS_OK; }
-    if (!strcmp(key, "field_early")) { h->opt_field_early = value; return NSFS_OK; }
     if (!strcmp(key, "field_fence")) { h->opt_field_fence = value; return NSFS_OK; }
     if (!strcmp(key, "field_merge")) { h->opt_field_merge = value; return NSFS_OK; }
     if (!strcmp(key, "field_sched_ns")) { h->opt_field_sched_ns = value; return NSFS_OK; }
-    if (!strcmp(key, "field_gate")) { h->opt_field_gate = value; return NSFS_OK; }
-    if (!strcmp(key, "field_groups")) { h->opt_field_groups = value; return NSFS_OK; }
-    if (!strcmp(key, "field_delta_in")) { h->opt_field_delta_in = value; return NSFS_OK; }
     if (!strcmp(key, "field_wait_ns")) { h->opt_field_wait_ns = value; return NSFS_OK; }
-    if (!strcmp(key, "field_alpha")) { h->opt_field_alpha = value; return NSFS_OK; }
     if (!strcmp(key, "active_row_lo")) { h->opt_active_row_lo = value; h->have_map = false; return NSFS_OK; }   // masks depend on it: set the map again
     if (!strcmp(key, "active_row_hi")) { h->opt_active_row_hi = value; h->have_map = false; return NSFS_OK; }
     if (!strcmp(key, "count_row_lo")) { h->opt_count_row_lo = value; return NSFS_OK; }

@@ -32,60 +32,55 @@ constexpr float  kSqrt2F = 1.41421356237309504880f;
 // in_mask[v]  (uint16): bits 0..7  in-edge d exists from the FREE cell v-OFF[d]; bits 8..15 it costs sqrt(2)
 constexpr uint32_t kThrowBit = 1u << 8;
 
-constexpr uint32_t kNoKey = 0x7f800000u;   // +inf as float bits: "no pending update" (non-negative floats order like their bits)
-constexpr int kFieldTile = 64;              // tile side of the field solvers (field.cu, field_bucket.cu)
+// ---- cost-to-go field (field.cu): Q17.15 fixed point ---------------------------------------------------------------------
+// g is kept as uint32 in units of 2^-15: the edge weights 1 and sqrt(2) become 32768 and 46341 (= round(sqrt(2) * 2^15); relative
+// error 1.08e-6), the reference's "infinity" 1e5 (astar.cpp:40) becomes kInfQ = 1e5 * 2^15 < 2^32.  Integer sums are exact and
+// order independent, so every scheduler / sharding returns the same bits and the error against the reference's fp64 sums stays
+// at 1.08e-6 relative for any path length (an fp32 plane drifts past 1e-5 beyond ~3000 steps).
+constexpr uint32_t kQOne = 32768u;
+constexpr uint32_t kQDiag = 46341u;
+constexpr uint32_t kInfQ = 3276800000u;      // 1e5 in Q17.15: exactly representable as fp32, converts back to 1e5f
+constexpr uint32_t kNoKey = 0xffffffffu;     // "no pending update" (every value and key is <= kInfQ + kQDiag)
+constexpr int kFieldTile = 64;               // tile side of the field solver
 
-// Parameters of the field solve kernels (field.cu: pull relaxation; field_bucket.cu: bucketed push expansion).
+// Parameters of the field solve kernel.
 struct FieldParams {
-    unsigned long long* prof;   // [8] cycle/iteration counters when NSFS_FIELD_PROF
-    float* g;
-    float* gx;            // bucket kernel: the value each cell was last expanded at (g < gx: the cell is open)
-    const uint16_t* out_mask;
-    long long win_lo, win_hi;   // bucket kernel: cells outside [win_lo, win_hi) take no in-edges (row-partitioned shards)
+    unsigned long long* prof;   // visit trace when built with NSFS_FIELD_TRACE (dev/trace_field.py), else nullptr
+    uint32_t* g;                // [N] Q17.15
     const uint16_t* in_mask;
     uint32_t* tile_key;   // per tile: smallest value a neighbour wrote into this tile's halo since it was last relaxed
-    int* list;
-    int* counts;          // 0: list length; 2: rounds; 3: tile visits; 4: error flag; 5: reached; 6: sweeps
+    int* counts;          // 1: pending tiles + visits in flight; 3: tile visits; 4: error flags; 5: reached; 6: smallest pending key
     int H, W;
     long long N;
     int tiles_x, tiles_y;
-    int max_rounds;
-    unsigned idle_ns;     // back-off of a warp that has nothing to relax
-    int inner;            // warp-local relaxations of an active sub-block per block-wide sweep
-    float delta;          // width of the cost band [.., thr] the wavefront may advance into per round (delta-stepping)
-    float alpha;          // thr_r = max(min pending key + delta, thr_{r-1} + alpha * delta)
-    float delta_in;       // ordered relaxation: a sub-block runs while its key is within delta_in of the tile's smallest due key
-    unsigned wait_ns;     // ... and otherwise waits this long before looking again
+    unsigned idle_ns;     // longest back-off of a warp that has nothing to relax
+    unsigned wait_ns;     // ... and the shortest, right after it had work
+    int inner;            // warp-local relaxation passes of a due sub-block before it yields
+    uint32_t delta;       // width (Q17.15) of the cost band [key, key + delta] a visit may advance into (delta-stepping over tiles)
     // peer-to-peer shards (NVLink): side 0 = the shard above (smaller rows), 1 = below.  A shard pushes every improvement
     // of its first / last two OWNED rows straight into the neighbour's ghost rows and wakes the neighbour's tiles.
     int* gcount;          // pending tiles + visits in flight: counts + 1, or ONE counter shared by all shards (on the owner's GPU)
-    float* peer_g[2];     // the neighbour's g array (its local rows), nullptr = no neighbour on that side
+    uint32_t* peer_g[2];  // the neighbour's g plane (its local rows), nullptr = no neighbour on that side
     uint32_t* peer_key[2];
     int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
     int peer_tiles_y[2];
     int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
-    uint32_t* blk_min;    // [gridDim.x] global gate: the smallest key each block still has to deal with (pending or in flight)
     unsigned sched_ns;    // back-off of a block that owns no pending tile
     int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
     int light;            // 1: key posts are release atomics (MEMBAR.ALL.GPU) instead of __threadfence (MEMBAR.SC.GPU + L1 invalidate) + atomicMin
-    int early;            // 1: border changes are posted to the neighbouring tiles during the visit, not at its end
-    float gate;           // a block leaves a tile alone while its key exceeds the smallest such key anywhere by more than this (0 = off)
-    int* tile_busy;       // dynamic scheduling: 1 while some block is relaxing the tile (a tile is never relaxed by two blocks at once)
-    int groups;           // dynamic scheduling: number of tile groups (see the scan loop)
-    int dynamic;          // 1: any block takes the pending tile with the smallest key; 0: tile t belongs to block t % gridDim.x
-    uint32_t cap;         // float bits: tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it
-                          // (kNoKey - 1 = no cap).  Used by the multi-GPU solve to advance all shards band by band.
+    uint32_t* blk_key;    // [workers] global gate: the smallest key each worker block holds (pending or in flight)
+    uint32_t* gfloor;     // ... and their minimum, kept by the grid's last block
+    uint32_t gate;        // a worker leaves a tile alone while its key exceeds *gfloor + gate (Q17.15; 0 = no gate)
+    uint32_t cap;         // tiles whose pending key exceeds it stay pending and nothing is relaxed beyond it (kNoKey - 1 = no cap).
+                          // Used by the multi-GPU solve to advance all shards band by band.
 };
 
 struct FieldWork {
-    float*    g = nullptr;         // [N]
-    float*    gx = nullptr;        // [N] bucket kernel: value at the last expansion (1e5 = never); allocated on first use
-    bool      gx_ready = false;    // the field in progress was begun with gx filled
+    uint32_t* g = nullptr;         // [N] Q17.15 during a solve; fp32 cost units (same buffer) once nsfs_field_finish has run
     uint8_t*  pred = nullptr;      // [N]
-    uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile (float bits), +inf bits = none
-    int*      list[2] = {nullptr, nullptr};
-    int*      tile_busy = nullptr; // [nTiles] dynamic scheduling: tile is being relaxed
-    int*      counts = nullptr;    // [8]: 0 list length, 1 pending (async), 2 rounds, 3 tile visits, 4 error flag, 5 reached, 6 min pending key, 7 thr
+    uint32_t* tile_key = nullptr;  // [nTiles] smallest pending halo update per tile, kNoKey = none
+    int*      counts = nullptr;    // [16]
+    uint32_t* blk_key = nullptr;   // global gate: per-block keys + the floor word
     int       tiles_x = 0, tiles_y = 0;
     int       src_i = -1, src_j = -1;
     bool      valid = false;       // solved and finished: nsfs_field_path may walk pred
@@ -97,13 +92,15 @@ struct FieldWork {
     int*      peer_counts = nullptr;          // the counter owner's counts array (nullptr: mine)
     void*     ipc_opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int       own_lo = 0, own_hi = 0;         // owned local rows (0, 0 = all)
-    float     min_pending = 0.f;   // smallest tile key left pending by the last relax (+inf = none)
-    bool      begun = false;       // g holds a field in progress (nsfs_field_begin or a full solve ran)
+    float     min_pending = 0.f;   // smallest tile key left pending by the last relax, in cost units (+inf = none)
+    bool      begun = false;       // g holds a field in progress (nsfs_field_begin ran, nsfs_field_finish has not)
+    bool      finished = false;    // g holds a finished field in fp32 cost units
 };
 
 struct SearchWork {
     // one slot per concurrently running query (one warp each)
     int       slots = 0;
+    int       target = 0;          // the slot count this allocation was made for (slots < target: free HBM clamped it)
     long long heap_cap = 0;        // entries per slot
     uint4*    cells = nullptr;     // [slots][N]   {g.lo, g.hi, parent key, (epoch << 1) | visited}
     unsigned long long* heap = nullptr;  // [slots][heap_cap]
@@ -114,6 +111,7 @@ struct SearchWork {
 struct TeamWork {
     // batch kernel (search_team.cu): one slot per team of 8 lanes, four teams per warp
     int       slots = 0;
+    int       target = 0;          // see SearchWork
     long long heap_cap = 0;
     uint2*    cells = nullptr;     // [slots][N]   {n_card | n_diag << 16, epoch << 4 | visited << 3 | parent direction}
     unsigned long long* heap = nullptr;
@@ -164,17 +162,14 @@ struct nsfs_planner {
     long long opt_field_inner = 0;      // 0 = default (16)
     long long opt_field_delta = 0;      // 0 = default (128)
     long long opt_graph = 0;            // 0 = the reference's quirk graph; 1 = textbook 8-connected grid
-    long long opt_field_mode = 0;       // 0 = asynchronous, tile t owned by block t % grid; 1 = bulk-synchronous rounds; 2 = asynchronous with dynamic tile claiming
+    long long opt_field_mode = 0;       // warps per resident tile: 0 = 4 (8 tiles per SM), 1 = 8 (4 tiles), 2 = 16 (2 tiles)
+    long long opt_field_tiles_per_sm = 0;   // cap on resident tiles per SM (0 = as many as fit)
+    long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
     long long opt_field_idle_ns = 0;    // 0 = default (1000)
-    long long opt_field_alpha = -1;     // percent; < 0 = default (50); bulk-synchronous variant only
     long long opt_field_fence = 0;      // 0 = __threadfence before key posts, 1 = release atomics (lighter fence, no L1 invalidate)
-    long long opt_field_early = 0;      // post border changes to neighbouring tiles during a visit (cut-through): 0 / 1 = on, 2 = off
     long long opt_field_merge = 0;      // a visit absorbs posts that arrive for its own tile before it ends: 0 / 1 = on, 2 = off
     long long opt_field_sched_ns = 0;   // back-off of a block with no pending tile (0 = default 400)
-    long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
-    long long opt_field_groups = 0;     // dynamic tile scheduling: tile groups (0 = default)
-    long long opt_field_delta_in = 0;   // ordered in-tile relaxation: band of due keys that may run (0 = no tile-wide gate)
-    long long opt_field_wait_ns = 0;    // ... back-off of a warp whose due sub-block is ahead of that band (0 = default 200)
+    long long opt_field_wait_ns = 0;    // shortest back-off of a warp with nothing due, right after it had work (0 = default 200)
     // row-partitioned shards: rows outside [active_row_lo, active_row_hi) take no in-edges (they only exist
     // so the masks of the rows next to them see the right neighbourhood); counts cover [count_row_lo, count_row_hi)
     long long opt_active_row_lo = 0, opt_active_row_hi = 0;   // hi == 0: all rows
@@ -197,7 +192,6 @@ int launch_field(nsfs_planner* h, int si, int sj, nsfs_stats* st);
 int launch_field_begin(nsfs_planner* h, int si, int sj);
 int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_vals, int* d_improved);
 int launch_field_relax(nsfs_planner* h, float cap);
-int launch_field_relax_bucket(nsfs_planner* h, FieldParams p);
 int launch_field_relax_p2p(nsfs_planner* h);
 int launch_field_count_pending(nsfs_planner* h);
 int launch_field_finish(nsfs_planner* h);

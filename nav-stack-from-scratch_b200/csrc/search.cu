@@ -174,6 +174,14 @@ __device__ __forceinline__ unsigned long long make_entry(double g, double h, uin
     return (fi << (kKeyBits + kGBits)) | (gi << kKeyBits) | (unsigned long long)key;
 }
 
+// An open-list entry holds (int)f in 18 bits and (int)g in 17: g stays below the reference's "infinity" 1e5 < 2^17, but f = g + h
+// grows with the heuristic, and the goal is the caller's (an off-grid or very distant goal, a very elongated map).  A key that
+// does not fit would wrap and silently change the pop order, so such a query ends with NSFS_E_HEAP instead.
+__device__ __forceinline__ bool entry_overflows(double g, double h, int mode) {
+    const double f = (mode == NSFS_MODE_G) ? 0.0 : __dadd_rn(g, h);
+    return !(f < (double)(1 << kGBits << 1)) || !(g < (double)(1 << kGBits));
+}
+
 // Warp-parallel isLos (grid_planner_core.cpp:481-496) over the closed form of bresenham_los
 // (bot_utils.cpp:137-192): cell t of the ray has l = l0 + t*dl, s = s0 + ds*floor((2t|Ds|+|Dl|)/(2|Dl|)).
 // Both end points are in-range cells here, so no ray cell can leave the grid.
@@ -237,8 +245,12 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(
         } else {
             if (lane == 0) __stcg(cells + ks, make_cell(0.0, ks, epoch << 1));
             __syncwarp();
-            heap_push(heap, n, make_entry(0.0, heuristic<ALGO>(si, sj, gi, gj), ks, mode), prio, lane);
-            pushes = 1; peak = 1;
+            const double h0 = heuristic<ALGO>(si, sj, gi, gj);
+            if (entry_overflows(0.0, h0, mode)) status = NSFS_E_HEAP;
+            else {
+                heap_push(heap, n, make_entry(0.0, h0, ks, mode), prio, lane);
+                pushes = 1; peak = 1;
+            }
         }
 
         while (status == NSFS_OK && n > 0) {
@@ -348,7 +360,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(
                     const double pg = __shfl_sync(0xffffffffu, cand, src);
                     if ((long long)n >= p.heap_cap) { status = NSFS_E_HEAP; break; }
                     const int vi = __shfl_sync(0xffffffffu, vi_mine, src), vj = __shfl_sync(0xffffffffu, vj_mine, src);
-                    heap_push(heap, n, make_entry(pg, heuristic<ALGO>(vi, vj, gi, gj), pk, mode), prio, lane);
+                    const double ph = heuristic<ALGO>(vi, vj, gi, gj);
+                    if (entry_overflows(pg, ph, mode)) { status = NSFS_E_HEAP; break; }
+                    heap_push(heap, n, make_entry(pg, ph, pk, mode), prio, lane);
                     pushes++;
                     if (n > peak) peak = n;
                 }
@@ -546,16 +560,19 @@ int search_alloc(nsfs_planner* h, int want_slots) {
     long long heap_cap = h->opt_heap_cap > 0 ? h->opt_heap_cap : h->N + 8;
     if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;            // heap positions are 32-bit
     if (want_slots < 1) want_slots = 1;
-    if (s.cells && s.slots >= want_slots && s.heap_cap >= heap_cap) return NSFS_OK;
+    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots : (long long)h->sm_count * 32;
+    long long slots = want_slots;
+    if (slots > cap) slots = cap;
+    // reuse: enough slots, or an allocation that was made for at least this many and clamped by free HBM (asking again would
+    // only free and re-allocate the same ~100 GB)
+    if (s.cells && s.heap_cap >= heap_cap && (s.slots >= slots || s.target >= slots)) return NSFS_OK;
     search_free(h);
     size_t free_b = 0, total_b = 0;
     NSFS_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
     const long long heap_stride = (heap_cap + 5) & ~1ll;
     const size_t per_slot = (size_t)h->N * sizeof(uint4) + (size_t)heap_stride * sizeof(unsigned long long);
     long long fit = (long long)((double)free_b * 0.80 / (double)per_slot);
-    long long cap = h->opt_max_slots > 0 ? h->opt_max_slots : (long long)h->sm_count * 32;
-    long long slots = want_slots;
-    if (slots > cap) slots = cap;
+    const long long target = slots;
     if (slots > fit) slots = fit;
     if (slots < 1) return NSFS_E_NOMEM;
     NSFS_CUDA_TRY(h, cudaMalloc(&s.cells, (size_t)slots * (size_t)h->N * sizeof(uint4)));
@@ -565,6 +582,7 @@ int search_alloc(nsfs_planner* h, int want_slots) {
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * (size_t)h->N * sizeof(uint4), h->stream));
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.epoch, 0, (size_t)slots * sizeof(uint32_t), h->stream));
     s.slots = (int)slots;
+    s.target = (int)target;
     s.heap_cap = heap_cap;
     return NSFS_OK;
 }

@@ -6,8 +6,15 @@
 // query in lockstep with the other three, so the same bookkeeping instructions advance four open lists at once.
 // Eight lanes are also exactly the 8 neighbours of an expansion.
 //
-// What is replayed is unchanged (see search.cu): libstdc++'s push_heap / pop_heap on 64-bit entries f:18 | g:17 | key:29
-// with the reference's three comparators, int-truncated keys, pushes in NB_LUT order, closed cells re-labelled.
+// What is replayed is unchanged (see search.cu): libstdc++'s push_heap / pop_heap with the reference's three comparators,
+// int-truncated keys, pushes in NB_LUT order, closed cells re-labelled.  Entries here are 64-bit words
+//   high word  (int)f : 16 | (int)g : 16        low word  flat key (29 bits)
+// so a comparator is ONE 32-bit compare on the high word (f: hi >> 16, g: hi & 0xffff, fg: hi), chosen at compile time
+// (the cost mode is a template parameter).  An f or g beyond 16 bits ends the query with NSFS_E_HEAP like a step-count
+// overflow (re-run on the wide kernel, whose entries hold f:18 | g:17).
+// The top seven levels of every open list (positions 1..127, 1 KB per team) live in SHARED memory: a sift-down starts with
+// two 3-level chunks at shared-memory latency, the root is read without a trip to L2 / HBM, and a push that rises into the
+// top meets it there (ncu round 1: ~8 dependent global round trips per pop, long_scoreboard the first stall).
 //   pop   3-level chunks: team lane t < 7 owns internal node t of the subtree under the hole and loads both children
 //         with one 128-bit load; two ballots give the path through the three levels; stop at the first picked child that
 //         sorts after the displaced element (same final array as sink-to-leaf + sift-up, priorities are monotone on a path)
@@ -25,10 +32,9 @@
 
 namespace nsfs {
 
-constexpr int kKeyBitsT = 29, kGBitsT = 17;
-constexpr unsigned long long kKeyMaskT = (1ull << kKeyBitsT) - 1ull;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TEAM_WARPS_PER_BLOCK = 4;
+constexpr uint32_t kTopN = 128;          // heap positions < kTopN are held in shared memory (levels 0..6)
 enum { PH_FETCH = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINAL = 3, PH_DONE = 4 };
 
 struct TeamParams {
@@ -52,25 +58,42 @@ struct TeamParams {
     int32_t* paths;               // optional [nq][path_cap][2]
     int path_cap;
     long long* stats5;
+    uint32_t div_m;               // key / W = __umulhi(key, div_m) >> div_s, exact for key < 2^29 (set by the launcher)
+    int div_s;
 };
 
-struct PrioT {
-    int sh;
-    unsigned long long msk;
-    __device__ __forceinline__ unsigned long long operator()(unsigned long long e) const { return (e >> sh) & msk; }
-};
+// the selected comparator's sort key, from an entry's high word
+template <int MODE>
+__device__ __forceinline__ uint32_t prio_of(unsigned long long e) {
+    const uint32_t hi = (uint32_t)(e >> 32);
+    if (MODE == NSFS_MODE_F) return hi >> 16;            // f only            (grid_planner_core.cpp:55-59)
+    if (MODE == NSFS_MODE_G) return hi & 0xffffu;        // g only            (61-65)
+    return hi;                                           // f, then smaller g (67-75)
+}
 
 __device__ __forceinline__ unsigned team_ballot(bool pred, int tbase) { return (__ballot_sync(FULL, pred) >> tbase) & 0xffu; }
 
+// One open list: positions < kTopN in shared memory (s), the rest in global memory (a); position = heap index + 1.
+struct TeamHeap {
+    unsigned long long* a;
+    unsigned long long* s;
+    __device__ __forceinline__ unsigned long long ld(uint32_t pos) const { return pos < kTopN ? s[pos] : a[pos]; }
+    __device__ __forceinline__ void st(uint32_t pos, unsigned long long v) const { if (pos < kTopN) s[pos] = v; else a[pos] = v; }
+    __device__ __forceinline__ ulonglong2 ld_pair(uint32_t lpos) const {     // lpos even: both children on the same side of kTopN
+        return lpos < kTopN ? *reinterpret_cast<const ulonglong2*>(s + lpos) : *reinterpret_cast<const ulonglong2*>(a + lpos);
+    }
+};
+
 // std::pop_heap for every team with act set (each on its own array); warp-uniform control flow.
-__device__ __forceinline__ void team_pop(unsigned long long* a, uint32_t& n, bool act, const PrioT prio, int tl, int tbase, int r, uint32_t o) {
-    uint32_t len = 0;
-    unsigned long long v = 0, pv = 0;
+template <int MODE>
+__device__ __forceinline__ void team_pop(const TeamHeap hp, uint32_t& n, bool act, int tl, int tbase, int r, uint32_t o) {
+    uint32_t len = 0, pv = 0;
+    unsigned long long v = 0;
     bool sinking = false;
     if (act) {
         len = n - 1u;
         n = len;
-        if (len > 0u) { v = a[len + 1u]; pv = prio(v); sinking = true; }
+        if (len > 0u) { v = hp.ld(len + 1u); pv = prio_of<MODE>(v); sinking = true; }
     }
     uint32_t c1 = 1u;                                     // position (heap index + 1) of the hole
     while (__any_sync(FULL, sinking)) {
@@ -78,10 +101,10 @@ __device__ __forceinline__ void team_pop(unsigned long long* a, uint32_t& n, boo
         const uint32_t lpos = 2u * pos;
         const bool has = sinking && tl < 7 && (c1 >> (30 - r)) == 0u && lpos <= len;
         ulonglong2 ch = make_ulonglong2(0ull, 0ull);
-        if (has) ch = *reinterpret_cast<const ulonglong2*>(a + lpos);
-        const bool left = !(lpos + 1u <= len) || prio(ch.y) > prio(ch.x);      // right child unless it sorts after the left one
+        if (has) ch = hp.ld_pair(lpos);
+        const bool left = !(lpos + 1u <= len) || prio_of<MODE>(ch.y) > prio_of<MODE>(ch.x);      // right child unless it sorts after the left one
         const unsigned long long pick = left ? ch.x : ch.y;
-        const bool stop = !has || prio(pick) > pv;
+        const bool stop = !has || prio_of<MODE>(pick) > pv;
         const unsigned m_left = team_ballot(left, tbase);
         const unsigned m_stop = team_ballot(stop, tbase);
         uint32_t node = 0, steps = 0, path = 0;
@@ -92,11 +115,11 @@ __device__ __forceinline__ void team_pop(unsigned long long* a, uint32_t& n, boo
             node = 2u * node + 2u - ((m_left >> node) & 1u);
             ++steps;
         }
-        if (sinking && ((path >> tl) & 1u)) a[pos] = pick;
+        if (sinking && ((path >> tl) & 1u)) hp.st(pos, pick);
         const int rq = 31 - __clz(node + 1u);
         const uint32_t npos = (c1 << rq) + (node + 1u - (1u << rq));
         if (sinking) {
-            if (steps < 3u) { if (tl == 0) a[npos] = v; sinking = false; }
+            if (steps < 3u) { if (tl == 0) hp.st(npos, v); sinking = false; }
             else c1 = npos;
         }
         __syncwarp();
@@ -104,20 +127,21 @@ __device__ __forceinline__ void team_pop(unsigned long long* a, uint32_t& n, boo
 }
 
 // std::push_heap for every team with pushing set.
-__device__ __forceinline__ void team_push(unsigned long long* a, uint32_t& n, unsigned long long v, bool pushing, const PrioT prio, int tl, int tbase) {
+template <int MODE>
+__device__ __forceinline__ void team_push(const TeamHeap hp, uint32_t& n, unsigned long long v, bool pushing, int tl, int tbase) {
     uint32_t base = n + 1u;                               // position of the hole the new element rises from
-    const unsigned long long pv = prio(v);
+    const uint32_t pv = prio_of<MODE>(v);
     bool rising = pushing;
     while (__any_sync(FULL, rising)) {
         const uint32_t q = base >> tl;                    // tl >= 1: position of the tl-th ancestor of the hole
         const bool valid = rising && tl >= 1 && q >= 1u;
         unsigned long long e = 0;
-        if (valid) e = a[q];
-        const unsigned rise = team_ballot(valid && prio(e) > pv, tbase);
+        if (valid) e = hp.ld(q);
+        const unsigned rise = team_ballot(valid && prio_of<MODE>(e) > pv, tbase);
         const int m = __ffs(~(rise >> 1)) - 1;            // run of ancestors (from the parent up) that sort after v: 0..7
-        if (rising && tl >= 1 && tl <= m) a[base >> (tl - 1)] = e;
+        if (rising && tl >= 1 && tl <= m) hp.st(base >> (tl - 1), e);
         if (rising) {
-            if (m < 7) { if (tl == 0) a[base >> m] = v; rising = false; }
+            if (m < 7) { if (tl == 0) hp.st(base >> m, v); rising = false; }
             else base >>= 7;                              // seven levels up and still rising
         }
         __syncwarp();
@@ -125,19 +149,19 @@ __device__ __forceinline__ void team_push(unsigned long long* a, uint32_t& n, un
     if (pushing) n = n + 1u;
 }
 
-template <int ALGO>
+template <int ALGO, int MODE>
 __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(TeamParams p) {
+    __shared__ __align__(16) unsigned long long s_top[TEAM_WARPS_PER_BLOCK * 4][kTopN];
     const int lane = threadIdx.x & 31, tl = lane & 7, tbase = lane & 24;
     const int slot = (blockIdx.x * TEAM_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * 4 + (lane >> 3);
-    const int W = p.W, mode = p.mode;
+    const int W = p.W;
+    constexpr int mode = MODE;
     const uint32_t uW = (uint32_t)W, uN = (uint32_t)p.N;
     const bool have_slot = slot < p.slots;
     uint2* cells = p.cells + (size_t)(have_slot ? slot : 0) * (size_t)p.N;
-    unsigned long long* heap = p.heap + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
-    PrioT prio;
-    if (mode == NSFS_MODE_F) { prio.sh = kKeyBitsT + kGBitsT; prio.msk = ~0ull; }
-    else if (mode == NSFS_MODE_G) { prio.sh = kKeyBitsT; prio.msk = (1ull << kGBitsT) - 1ull; }
-    else { prio.sh = kKeyBitsT; prio.msk = ~0ull; }
+    TeamHeap heap;
+    heap.a = p.heap + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
+    heap.s = s_top[(threadIdx.x >> 5) * 4 + (lane >> 3)];
     const int nr = 31 - __clz(tl + 1);                    // my node of a 3-level subtree: level 0,1,1,2,2,2,2 (lane 7: unused)
     const uint32_t no = (uint32_t)(tl + 1) - (1u << nr);
     const int my_di = nb_di(tl), my_dj = nb_dj(tl);
@@ -176,13 +200,16 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                             const int ax = abs(gi - si), ay = abs(gj - si);        // dist_oct's slip: both against the ROW (bot_utils.cpp:47)
                             h0 = __dadd_rn(__dmul_rn((double)min(ax, ay), kSqrt2D), (double)abs(ax - ay));
                         }
-                        const unsigned long long f0 = (mode == NSFS_MODE_G) ? 0ull : (unsigned long long)(unsigned)__double2int_rz(h0);
-                        if (tl == 0) {
-                            __stcg(cells + ks, make_uint2(0u, epoch << 4));
-                            heap[1] = (f0 << (kKeyBitsT + kGBitsT)) | (unsigned long long)ks;
+                        const uint32_t f0 = (mode == NSFS_MODE_G) ? 0u : (uint32_t)__double2int_rz(h0);
+                        if (f0 > 0xffffu) { status = NSFS_E_HEAP; phase = PH_FINAL; }       // beyond the 16-bit sort key: the wide kernel replays it
+                        else {
+                            if (tl == 0) {
+                                __stcg(cells + ks, make_uint2(0u, epoch << 4));
+                                heap.st(1u, ((unsigned long long)(f0 << 16) << 32) | (unsigned long long)ks);
+                            }
+                            n = 1; pushes = 1; peak = 1;
+                            phase = PH_SEARCH;
                         }
-                        n = 1; pushes = 1; peak = 1;
-                        phase = PH_SEARCH;
                     }
                 }
             }
@@ -194,9 +221,9 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
         {
             const bool act = phase == PH_SEARCH;
             unsigned long long top = 0;
-            if (act) top = heap[1];
-            const uint32_t ku = (uint32_t)(top & kKeyMaskT);
-            const int i = (int)(ku / uW), j = (int)(ku - (uint32_t)i * uW);
+            if (act) top = heap.s[1];                                // the root is always in shared memory
+            const uint32_t ku = (uint32_t)top;
+            const int i = (int)(__umulhi(ku, p.div_m) >> p.div_s), j = (int)(ku - (uint32_t)i * uW);
             const uint32_t kv = ku + (uint32_t)my_off;               // my neighbour: flat key; its row follows the column wrap
             int vi = i + my_di;
             { const int vj = j + my_dj; if (vj >= W) vi++; else if (vj < 0) vi--; }
@@ -207,7 +234,12 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 if (tl == 0) cu_l = __ldcg(cells + ku);
                 if (tl == 1) om_l = __ldg(p.out_mask + ku);
             }
-            team_pop(heap, n, act, prio, tl, tbase, nr, no);
+            if (act && tl >= 1 && n > kTopN) {
+                // the first push after this pop rises from position n (= n_after_pop + 1): start its ancestors on their way
+                const uint32_t q = n >> tl;
+                if (q >= kTopN) asm volatile("prefetch.global.L1 [%0];" :: "l"(heap.a + q));
+            }
+            team_pop<MODE>(heap, n, act, tl, tbase, nr, no);
             uint2 cu;
             cu.x = __shfl_sync(FULL, cu_l.x, 0, 8); cu.y = __shfl_sync(FULL, cu_l.y, 0, 8);
             const uint32_t om = __shfl_sync(FULL, om_l, 1, 8);
@@ -245,8 +277,9 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                             }
                             f = __dadd_rn(cand, h);
                         }
-                        entry = ((unsigned long long)(unsigned)__double2int_rz(f) << (kKeyBitsT + kGBitsT)) |
-                                ((unsigned long long)(unsigned)__double2int_rz(cand) << kKeyBitsT) | (unsigned long long)kv;
+                        const uint32_t fi = (uint32_t)__double2int_rz(f), gi32 = (uint32_t)__double2int_rz(cand);
+                        if (fi > 0xffffu || gi32 > 0xffffu) { overflow = true; relax = false; }     // (the record is written; the query is abandoned anyway)
+                        entry = ((unsigned long long)((fi << 16) | (gi32 & 0xffffu)) << 32) | (unsigned long long)kv;
                     }
                 }
             }
@@ -259,7 +292,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 rb &= rb - 1u;
                 const unsigned long long v = __shfl_sync(FULL, entry, src, 8);
                 if (pushing && (long long)n >= p.heap_cap) { status = NSFS_E_HEAP; pushing = false; rb = 0; phase = PH_FINAL; }
-                team_push(heap, n, v, pushing, prio, tl, tbase);
+                team_push<MODE>(heap, n, v, pushing, tl, tbase);
                 if (pushing) { pushes++; if (n > peak) peak = n; }
             }
             if (phase == PH_SEARCH && n == 0u) phase = PH_FINAL;        // open list exhausted: unreachable (astar.cpp:129-135)
@@ -385,8 +418,10 @@ int team_alloc(nsfs_planner* h, int want_slots) {
     const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * 28 * 4;    // 28 warps / SM x 4 teams: what 0.85 of a B200's HBM
                                                                                                            // holds at 1024^2 (9 MB per slot); 24 -> 28 warps measured +6 % queries/s
     long long slots = want_slots < cap ? want_slots : cap;
-    if (s.cells && s.slots >= slots && s.heap_cap >= heap_cap) return NSFS_OK;
+    // reuse: enough slots, or an allocation made for at least this many that free HBM clamped (see search_alloc)
+    if (s.cells && s.heap_cap >= heap_cap && (s.slots >= slots || s.target >= slots)) return NSFS_OK;
     team_free(h);
+    const long long target = slots;
     size_t free_b = 0, total_b = 0;
     NSFS_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
     const long long heap_stride = (heap_cap + 5) & ~1ll;
@@ -401,6 +436,7 @@ int team_alloc(nsfs_planner* h, int want_slots) {
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * (size_t)h->N * sizeof(uint2), h->stream));
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.epoch, 0, (size_t)slots * sizeof(uint32_t), h->stream));
     s.slots = (int)slots;
+    s.target = (int)target;
     s.heap_cap = heap_cap;
     return NSFS_OK;
 }
@@ -439,10 +475,30 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     const int block = TEAM_WARPS_PER_BLOCK * 32;
     const int per_block = TEAM_WARPS_PER_BLOCK * 4;
     const int grid = (p.slots + per_block - 1) / per_block;
+    {   // exact division of a flat key by W (key < 2^29): q = umulhi(key, m) >> s with m = ceil(2^(32+s) / W), 32 + s >= 29 + ceil(log2 W)
+        int l = 0;
+        while ((1ll << l) < (long long)h->W) ++l;
+        int sh = 29 + l - 32;
+        if (sh < 0) sh = 0;
+        const unsigned long long two = 1ull << (32 + sh);
+        p.div_m = (uint32_t)((two + (unsigned long long)h->W - 1ull) / (unsigned long long)h->W);
+        p.div_s = sh;
+    }
+    if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA) return NSFS_E_ARG;
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
-    if (algo == NSFS_ASTAR) search_team_kernel<NSFS_ASTAR><<<grid, block, 0, h->stream>>>(p);
-    else if (algo == NSFS_DJIKSTRA) search_team_kernel<NSFS_DJIKSTRA><<<grid, block, 0, h->stream>>>(p);
-    else return NSFS_E_ARG;
+    // 16 KB of shared memory per block (the open lists' top levels) x 7 resident blocks: ask for a carveout that holds them
+#define NSFS_TEAM_LAUNCH(A, M) do { cudaFuncSetAttribute(search_team_kernel<A, M>, cudaFuncAttributePreferredSharedMemoryCarveout, 60); \
+                                    search_team_kernel<A, M><<<grid, block, 0, h->stream>>>(p); } while (0)
+    if (algo == NSFS_ASTAR) {
+        if (p.mode == NSFS_MODE_F) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_F);
+        else if (p.mode == NSFS_MODE_G) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_G);
+        else NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_FG);
+    } else {
+        if (p.mode == NSFS_MODE_F) NSFS_TEAM_LAUNCH(NSFS_DJIKSTRA, NSFS_MODE_F);
+        else if (p.mode == NSFS_MODE_G) NSFS_TEAM_LAUNCH(NSFS_DJIKSTRA, NSFS_MODE_G);
+        else NSFS_TEAM_LAUNCH(NSFS_DJIKSTRA, NSFS_MODE_FG);
+    }
+#undef NSFS_TEAM_LAUNCH
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());

@@ -209,6 +209,38 @@ BatchPlan GpuPlannerBase::planBatch(const std::vector<int32_t>& sg4, MapData& ma
     return out;
 }
 
+BatchPlan GpuPlannerBase::planBatchSharded(DeviceGroup& group, const std::vector<int32_t>& sg4, MapData& map_data, int root) {
+    ensureHandle(map_data);
+    if (group.rank() == root) uploadMap(map_data);
+    int rc = nsfs_group_broadcast_map(group.raw(), handle_, root);
+    if (rc != NSFS_OK) fail(rc, "nsfs_group_broadcast_map");
+    const int nq = (int)(sg4.size() / 4);
+    BatchPlan out;
+    out.status.assign((size_t)nq, 0); out.path_len.assign((size_t)nq, 0); out.g_goal.assign((size_t)nq, 0.0); out.settled.assign((size_t)nq, 0);
+    if (!nq) return out;
+    rc = nsfs_group_plan_batch(group.raw(), handle_, algoCode(), modeCode(cost_mode_), nq, sg4.data(), out.status.data(), out.g_goal.data(),
+                               out.path_len.data(), out.settled.data(), &out.stats);
+    if (rc != NSFS_OK) fail(rc, "nsfs_group_plan_batch");
+    stats_ = out.stats;
+    return out;
+}
+
+// ---- DeviceGroup ------------------------------------------------------------------------------------------
+std::vector<unsigned char> DeviceGroup::makeId() {
+    std::vector<unsigned char> id(128);
+    if (nsfs_group_unique_id(id.data()) != NSFS_OK) throw std::runtime_error("nsfs_group_unique_id: NCCL (libnccl.so.2) is not available");
+    return id;
+}
+DeviceGroup::DeviceGroup(const std::vector<unsigned char>& id, int rank, int world, int device) {
+    if (id.size() != 128) throw std::invalid_argument("a group id is 128 bytes");
+    const int rc = nsfs_group_create(&g_, id.data(), rank, world, device);
+    if (rc != NSFS_OK) { g_ = nullptr; throw std::runtime_error(std::string("nsfs_group_create: ") + nsfs_strerror(rc)); }
+}
+DeviceGroup::~DeviceGroup() { if (g_) nsfs_group_destroy(g_); }
+void DeviceGroup::barrier() {
+    if (nsfs_group_barrier(g_) != NSFS_OK) throw std::runtime_error(std::string("nsfs_group_barrier: ") + nsfs_group_error(g_));
+}
+
 // ---- children ---------------------------------------------------------------------------------------------
 std::vector<Pos2D> GpuAstar::plan(Index idx_start, Index idx_goal, MapData& map_data) { return runPlan(NSFS_ASTAR, idx_start, idx_goal, map_data); }
 std::vector<Pos2D> GpuAstar::plan(Pos2D pos_start, Pos2D pos_goal, MapData& map_data) {
@@ -443,6 +475,34 @@ int nsfsh_plan_batch_idx(void* p, int nq, const int32_t* sg4, int32_t* status, d
         if (!g) return 2;
         const std::vector<int32_t> q(sg4, sg4 + 4 * (size_t)nq);
         const nsfs_host::BatchPlan r = g->planBatch(q, s->map);
+        memcpy(status, r.status.data(), (size_t)nq * 4); memcpy(path_len, r.path_len.data(), (size_t)nq * 4);
+        memcpy(g_goal, r.g_goal.data(), (size_t)nq * 8); memcpy(settled, r.settled.data(), (size_t)nq * 8);
+        if (gpu_ms) *gpu_ms = r.stats.gpu_ms;
+        return 0;
+    } catch (const std::out_of_range& e) { s->error = e.what(); return 1; }
+    catch (const std::exception& e) { s->error = e.what(); return 2; }
+}
+
+// A DeviceGroup for the session (rank 0 made the id with nsfsh_group_id and shipped it to the other ranks)
+int nsfsh_group_id(unsigned char* id128) {
+    try { const auto id = nsfs_host::DeviceGroup::makeId(); memcpy(id128, id.data(), 128); return 0; }
+    catch (const std::exception&) { return 2; }
+}
+void* nsfsh_group_create(const unsigned char* id128, int rank, int world, int device) {
+    try { return new nsfs_host::DeviceGroup(std::vector<unsigned char>(id128, id128 + 128), rank, world, device); }
+    catch (const std::exception&) { return nullptr; }
+}
+void nsfsh_group_destroy(void* g) { delete static_cast<nsfs_host::DeviceGroup*>(g); }
+
+// GpuPlannerBase::planBatchSharded: all nq queries in, all nq results out on every rank
+int nsfsh_plan_batch_sharded(void* p, void* group, int nq, const int32_t* sg4, int32_t* status, double* g_goal, int32_t* path_len,
+                             long long* settled, double* gpu_ms) {
+    auto* s = static_cast<Session*>(p);
+    try {
+        auto* g = dynamic_cast<nsfs_host::GpuPlannerBase*>(s->main_planner.get());
+        if (!g || !group) return 2;
+        const std::vector<int32_t> q(sg4, sg4 + 4 * (size_t)nq);
+        const nsfs_host::BatchPlan r = g->planBatchSharded(*static_cast<nsfs_host::DeviceGroup*>(group), q, s->map);
         memcpy(status, r.status.data(), (size_t)nq * 4); memcpy(path_len, r.path_len.data(), (size_t)nq * 4);
         memcpy(g_goal, r.g_goal.data(), (size_t)nq * 8); memcpy(settled, r.settled.data(), (size_t)nq * 8);
         if (gpu_ms) *gpu_ms = r.stats.gpu_ms;

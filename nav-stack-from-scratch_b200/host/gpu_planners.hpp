@@ -53,6 +53,9 @@ public:
     void setTextbookGraph(bool on);
     // nq independent plan(Index, Index, map) calls of this child on one upload of the map (sg4 = {si, sj, gi, gj} per query)
     BatchPlan planBatch(const std::vector<int32_t>& sg4, bot_utils::MapData& map_data);
+    // The same batch split over a DeviceGroup: `root` uploads its MapData and broadcasts the packed map, every rank plans its
+    // slice on its own GPU and every rank receives all results.  map_data is read on the root only.
+    BatchPlan planBatchSharded(class DeviceGroup& group, const std::vector<int32_t>& sg4, bot_utils::MapData& map_data, int root = 0);
     const nsfs_stats& lastStats() const { return stats_; }
     double lastGoalCost() const { return last_g_goal_; }   // nodes[goal].g of the last plan (1e5 = unreachable)
     // The path consumer's check of a trajectory against the current map: Commander::checkTrajectorySafety
@@ -135,6 +138,24 @@ protected:
     int algoCode() const override { return NSFS_THETASTAR; }
     std::vector<bot_utils::Pos2D> plan(bot_utils::Index idx_start, bot_utils::Index idx_goal, bot_utils::MapData& map_data) override;
     std::vector<bot_utils::Pos2D> plan(bot_utils::Pos2D pos_start, bot_utils::Pos2D pos_goal, bot_utils::MapData& map_data) override;
+};
+
+// ---- several GPUs, one planner process per GPU ------------------------------------------------------
+// RAII over nsfs_group_*: the NCCL communicator, the map broadcast and the gather of batch results all happen below the
+// C-ABI, so a GlobalPlanner-side caller needs nothing but the 128-byte group id from rank 0.
+class DeviceGroup {
+public:
+    static std::vector<unsigned char> makeId();                                   // rank 0
+    DeviceGroup(const std::vector<unsigned char>& id, int rank, int world, int device);
+    ~DeviceGroup();
+    DeviceGroup(const DeviceGroup&) = delete;
+    DeviceGroup& operator=(const DeviceGroup&) = delete;
+    int rank() const { return nsfs_group_rank(g_); }
+    int world() const { return nsfs_group_world(g_); }
+    void barrier();
+    nsfs_group_t* raw() const { return g_; }
+private:
+    nsfs_group_t* g_ = nullptr;
 };
 
 // ---- runtime selection (global_planner.cpp:102-130, 482-490) --------------------------------------------------

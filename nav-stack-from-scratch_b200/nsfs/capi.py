@@ -70,6 +70,19 @@ def lib():
         L.nsfs_last_path.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.nsfs_pin_host.argtypes = [vp, vp, C.c_size_t]
         L.nsfs_unpin_host.argtypes = [vp, vp]
+        L.nsfs_group_unique_id.argtypes = [vp]
+        L.nsfs_group_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+        L.nsfs_group_destroy.argtypes = [vp]
+        L.nsfs_group_destroy.restype = None
+        L.nsfs_group_rank.argtypes = [vp]
+        L.nsfs_group_world.argtypes = [vp]
+        L.nsfs_group_barrier.argtypes = [vp]
+        L.nsfs_group_error.argtypes = [vp]
+        L.nsfs_group_error.restype = C.c_char_p
+        L.nsfs_group_broadcast_map.argtypes = [vp, vp, i32]
+        L.nsfs_group_plan_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+        L.nsfs_group_field_attach.argtypes = [vp, vp, i32, i32, i32]
+        L.nsfs_group_field_solve.argtypes = [vp, vp, i32, i32, C.POINTER(C.c_longlong), C.POINTER(Stats)]
         L.nsfs_plan_batch.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_plan_batch_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Stats)]
         L.nsfs_field.argtypes = [vp, i32, i32, vp, vp, C.POINTER(Stats)]
@@ -111,6 +124,64 @@ def lib():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Group:
+    """nsfs_group_*: this rank of a one-process-per-GPU group (NCCL bound inside libnsfs_gpu.so).  ``dist`` (torch.distributed)
+    only carries the 128-byte id from rank 0 to the others."""
+
+    def __init__(self, dist, rank, world, device):
+        import torch
+        self.L = lib()
+        buf = np.zeros(128, np.uint8)
+        if rank == 0:
+            rc = self.L.nsfs_group_unique_id(buf.ctypes.data_as(C.c_void_p))
+            if rc != OK:
+                raise NsfsError(rc, "nsfs_group_unique_id (is libnccl.so.2 loadable?)")
+        t = torch.from_numpy(buf).to(torch.device("cuda", device))
+        dist.broadcast(t, src=0)
+        buf = np.ascontiguousarray(t.cpu().numpy())
+        self.g = C.c_void_p()
+        rc = self.L.nsfs_group_create(C.byref(self.g), buf.ctypes.data_as(C.c_void_p), int(rank), int(world), int(device))
+        if rc != OK:
+            self.g = None
+            raise NsfsError(rc, "nsfs_group_create")
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.nsfs_group_destroy(self.g)
+            self.g = None
+
+    def _check(self, rc, allow=()):
+        if rc != OK and rc not in allow:
+            raise NsfsError(rc, self.L.nsfs_strerror(rc).decode() + " | " + self.L.nsfs_group_error(self.g).decode())
+        return rc
+
+    def barrier(self):
+        self._check(self.L.nsfs_group_barrier(self.g))
+
+    def broadcast_map(self, planner, root=0):
+        self._check(self.L.nsfs_group_broadcast_map(self.g, planner.h, int(root)))
+
+    def plan_batch(self, planner, algo, mode, sg4):
+        sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)
+        nq = len(sg4)
+        status, plen = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        g, settled = np.zeros(nq, np.float64), np.zeros(nq, np.int64)
+        st = Stats()
+        self._check(self.L.nsfs_group_plan_batch(self.g, planner.h, ALGOS.get(algo, algo), MODES.get(mode, mode), nq, _ptr(sg4), _ptr(status),
+                                                 _ptr(g), _ptr(plen), _ptr(settled), C.byref(st)))
+        return dict(status=status, g_goal=g, path_len=plen, settled=settled, stats=st.asdict())
+
+    def field_attach(self, planner, held_lo, own_lo, own_hi):
+        self._check(self.L.nsfs_group_field_attach(self.g, planner.h, int(held_lo), int(own_lo), int(own_hi)))
+
+    def field_solve(self, planner, src):
+        reached, st = C.c_longlong(0), Stats()
+        rc = self.L.nsfs_group_field_solve(self.g, planner.h, int(src[0]), int(src[1]), C.byref(reached), C.byref(st))
+        self._check(rc, allow=(E_RANGE,))
+        return dict(status=rc, reached_total=reached.value, stats=st.asdict())
 
 
 class Planner:

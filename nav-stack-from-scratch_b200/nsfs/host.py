@@ -20,7 +20,8 @@ HOST_SO = os.path.join(PKG, "libnsfs_planners.so")
 SYMBOLS = ("nsfsh_create", "nsfsh_destroy", "nsfsh_error", "nsfsh_set_map", "nsfsh_generate_path_idx",
            "nsfsh_generate_path_pos", "nsfsh_find_better_point_pos", "nsfsh_find_better_point_idx", "nsfsh_load_config",
            "nsfsh_main_planner_kind", "nsfsh_sparsify", "nsfsh_plan_request", "nsfsh_check_trajectory", "nsfsh_set_graph", "nsfsh_set_map_sync",
-           "nsfsh_notify_map_changed", "nsfsh_plan_batch_idx")
+           "nsfsh_notify_map_changed", "nsfsh_plan_batch_idx", "nsfsh_group_id", "nsfsh_group_create", "nsfsh_group_destroy",
+           "nsfsh_plan_batch_sharded")
 
 _libs = {}
 
@@ -52,6 +53,12 @@ def lib(so_path=None):
         L.nsfsh_set_map_sync.argtypes = [vp, i32]
         L.nsfsh_notify_map_changed.argtypes = [vp]
         L.nsfsh_plan_batch_idx.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(dbl)]
+        L.nsfsh_group_id.argtypes = [vp]
+        L.nsfsh_group_create.argtypes = [vp, i32, i32, i32]
+        L.nsfsh_group_create.restype = vp
+        L.nsfsh_group_destroy.argtypes = [vp]
+        L.nsfsh_group_destroy.restype = None
+        L.nsfsh_plan_batch_sharded.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, C.POINTER(dbl)]
         _libs[path] = L
     return _libs[path]
 
@@ -76,6 +83,27 @@ def sparsify(xy, so_path=None):
 
 class PlannerError(RuntimeError):
     pass
+
+
+def make_group(dist, rank, world, device, so_path=None):
+    """A nsfs_host::DeviceGroup for this rank.  The NCCL id is made by rank 0 in C++ and travels over torch.distributed here
+    only because the test / bench driver already has it; a deployment ships the 128 bytes any way it likes."""
+    import torch
+    L = lib(so_path)
+    buf = np.zeros(128, np.uint8)
+    if rank == 0 and L.nsfsh_group_id(buf.ctypes.data_as(C.c_void_p)) != 0:
+        raise PlannerError("nsfs_group_unique_id failed: NCCL not available")
+    t = torch.from_numpy(buf).to(torch.device("cuda", device))
+    dist.broadcast(t, src=0)
+    buf = t.cpu().numpy()
+    g = L.nsfsh_group_create(buf.ctypes.data_as(C.c_void_p), rank, world, device)
+    if not g:
+        raise PlannerError("nsfs_group_create failed")
+    return g
+
+
+def destroy_group(group, so_path=None):
+    lib(so_path).nsfsh_group_destroy(group)
 
 
 class Session:
@@ -132,6 +160,20 @@ class Session:
         vp = C.c_void_p
         rc = self.L.nsfsh_plan_batch_idx(self.s, nq, sg4.ctypes.data_as(vp), status.ctypes.data_as(vp), g.ctypes.data_as(vp),
                                          plen.ctypes.data_as(vp), settled.ctypes.data_as(vp), C.byref(ms))
+        if rc != 0:
+            raise PlannerError(self.L.nsfsh_error(self.s).decode())
+        return dict(status=status, g_goal=g, path_len=plen, settled=settled, gpu_ms=ms.value)
+
+    def plan_batch_sharded(self, group, sg4):
+        """GpuPlannerBase::planBatchSharded over a DeviceGroup (see ``make_group``): all queries in, all results out on every rank."""
+        sg4 = np.ascontiguousarray(sg4, np.int32).reshape(-1, 4)
+        nq = len(sg4)
+        status, plen = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        g, settled = np.zeros(nq, np.float64), np.zeros(nq, np.int64)
+        ms = C.c_double(0)
+        vp = C.c_void_p
+        rc = self.L.nsfsh_plan_batch_sharded(self.s, group, nq, sg4.ctypes.data_as(vp), status.ctypes.data_as(vp), g.ctypes.data_as(vp),
+                                             plen.ctypes.data_as(vp), settled.ctypes.data_as(vp), C.byref(ms))
         if rc != 0:
             raise PlannerError(self.L.nsfsh_error(self.s).decode())
         return dict(status=status, g_goal=g, path_len=plen, settled=settled, gpu_ms=ms.value)

@@ -212,18 +212,19 @@ def test_fallback_in_shared_memory_agrees_with_the_wide_kernel(gpu_lib, oracle_m
 
 @pytest.mark.gpu
 def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
-    """The fp32 fixed point is unique, so the scheduling variants kept for A/B measurements (bulk-synchronous rounds with a
-    ballot-compacted tile list, dynamic tile claiming, other band widths) must agree bit for bit with the default."""
+    """The field is solved in exact integer arithmetic (Q17.15), so its fixed point cannot depend on the schedule: every
+    tile-residency setting (4 / 8 / 16 warps per resident tile, fewer resident tiles per SM), band width, pass budget, fence
+    flavour and the merged-visit switch must agree bit for bit with the default."""
     infl, lo = mapgen.synth_map(700, 900, 0.12, 93)
     src = mapgen.field_source(infl, lo)
     P = gpu_lib.Planner(700, 900)
     P.set_map(infl, lo)
     want = P.field(src)
-    for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_mode": 2, "field_groups": 1}, {"field_delta": 16}, {"field_delta": 100000},
-                 {"field_inner": 1}, {"field_delta_in": 8}, {"field_early": 2}, {"field_merge": 2}, {"field_early": 2, "field_merge": 2},
-                 {"field_gate": 64}, {"field_delta": 32, "field_inner": 2},
-                 {"field_mode": 3}, {"field_mode": 3, "field_delta": 6}, {"field_mode": 3, "field_delta": 40, "field_groups": 1}):
-        for k in ("field_mode", "field_groups", "field_delta", "field_inner", "field_delta_in", "field_early", "field_merge", "field_gate"):
+    keys = ("field_mode", "field_tiles_per_sm", "field_delta", "field_inner", "field_merge", "field_fence", "field_idle_ns", "field_wait_ns")
+    for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_tiles_per_sm": 1}, {"field_mode": 1, "field_tiles_per_sm": 3},
+                 {"field_delta": 16}, {"field_delta": 100000}, {"field_delta": 3, "field_inner": 2}, {"field_inner": 1}, {"field_merge": 2},
+                 {"field_fence": 1}, {"field_mode": 2, "field_merge": 2, "field_delta": 40}, {"field_idle_ns": 50, "field_wait_ns": 20}):
+        for k in keys:
             P.set_option(k, opts.get(k, 0))
         got = P.field(src)
         assert got["status"] == 0 and np.array_equal(got["g"], want["g"]) and np.array_equal(got["pred"], want["pred"]), opts

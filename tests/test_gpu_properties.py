@@ -50,22 +50,24 @@ def test_c2_field_2048_is_a_fixed_point_and_matches_probe_count(gpu_lib, oracle_
     OFF = np.array([W, W + 1, 1, -W + 1, -W, -W - 1, -1, W - 1])
     k = np.nonzero(reach & (pred != 255))[0]
     par = k - OFF[pred[k]]
-    # every reached cell hangs off a reached parent at exactly one fp32 step of cost 1 or sqrt(2)
+    # every reached cell hangs off a reached parent at exactly one step of cost 1 or sqrt(2): the solver works in Q17.15 integers
+    # (1 -> 32768, sqrt(2) -> 46341) and hands out fp32(q / 32768), so q is recovered to within the fp32 rounding of g (< 2^-23 relative)
     assert reach[par].all()
-    is1 = g[k] == g[par] + np.float32(1.0)
-    is2 = g[k] == g[par] + SQRT2F
-    assert (is1 | is2).all()
+    q = np.rint(g.astype(np.float64) * 32768.0)
+    tol = 2.0 + q[k] * 2.0 ** -22
+    step = q[k] - q[par]
+    assert ((np.abs(step - 32768.0) <= tol) | (np.abs(step - 46341.0) <= tol)).all()
     assert (reach & (pred == 255)).sum() == 1            # only the source has no predecessor
     # Bellman with the per-edge quirk weights (astar.cpp:88-123): the edge u -> u + OFF[d] exists iff the target is free and
-    # costs 1 if an even number of PASSABLE directions precede d at u, else sqrt(2); no in-edge may undercut g[v] (fp32 sums,
-    # the solver's own arithmetic).  On a framed map np.roll's wrap only touches the blocked frame.
+    # costs 1 if an even number of PASSABLE directions precede d at u, else sqrt(2); no in-edge may undercut g[v] (in the solver's
+    # own Q17.15 units, up to the fp32 rounding of the values handed out).  On a framed map np.roll's wrap only touches the blocked frame.
     npass = np.zeros(g.shape, np.int32)
     for d in range(8):
         tgt_free = np.roll(free, -OFF[d])                  # tgt_free[u] = free[u + OFF[d]]
-        w = np.where(npass % 2 == 0, np.float32(1.0), SQRT2F)
-        cand = np.roll(np.where(free & tgt_free & reach, g + w, np.float32(3e38)).astype(np.float32), OFF[d])   # cand[v] from u = v - OFF[d]
-        assert not (reach & (cand < g)).any(), d
-        assert not ((~reach) & free & (cand < 1e5)).any(), d          # an unreached free cell has no reached in-neighbour
+        w = np.where(npass % 2 == 0, 32768.0, 46341.0)
+        cand = np.roll(np.where(free & tgt_free & reach, q + w, 1e18), OFF[d])     # cand[v] from u = v - OFF[d]
+        assert not (reach & (cand < q - (2.0 + q * 2.0 ** -21))).any(), d
+        assert not ((~reach) & free & (cand < 1e17)).any(), d         # an unreached free cell has no reached in-neighbour
         npass += tgt_free & free
     for goal in mapgen.sample_free_cells(infl, lo, 8, 99):
         fp = P.field_path(goal)

@@ -1,6 +1,6 @@
 """Row-partitioned field on the GPU (SURVEY.md §8e / BASELINE C5): several shards of one map, each its own nsfs handle
-over its held rows, solved in lockstep on one device, against the single-handle field.  The fp32 fixed point is unique,
-so the bar is bit-identical g, identical predecessors and reached counts."""
+over its held rows, solved in lockstep on one device, against the single-handle field.  The field is solved in exact integer
+arithmetic, so the bar is bit-identical g, identical predecessors and reached counts."""
 import numpy as np
 import pytest
 
@@ -19,7 +19,7 @@ def _mono(gpu_lib, infl, lo, src):
 
 @pytest.mark.parametrize("spec", [(700, 520, 0.10, 51, True, 3), (260, 300, 0.22, 52, True, 4), (300, 130, 0.12, 53, False, 2)],
                          ids=["3-shards", "4-shards-dense", "2-shards-unframed-wrap"])
-@pytest.mark.parametrize("field_mode", [0, 3], ids=["pull-solver", "bucket-solver"])
+@pytest.mark.parametrize("field_mode", [0, 2], ids=["8-tiles-per-sm", "2-tiles-per-sm"])
 def test_sharded_field_is_bit_identical_to_one_handle(gpu_lib, spec, field_mode, monkeypatch):
     monkeypatch.setenv("NSFS_FIELD_MODE", str(field_mode))       # read by nsfs_create: every handle below uses that solver
     H, W, p, seed, frame, world = spec
@@ -113,3 +113,21 @@ def test_peer_to_peer_shards_over_nvlink():
            "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", "p2p_worker.py")]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-3000:]
+
+
+def test_group_entry_points_over_nccl():
+    """N >= 2 GPUs: nsfs_group_* (map broadcast, sharded batch with gathered results, row-block field with CUDA IPC attach) and
+    the C++ nsfs_host::DeviceGroup / planBatchSharded above them, against the single-GPU calls: identical arrays."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on one node")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29300 + os.getpid() % 300), os.path.join(root, "tests", "group_worker.py")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "GROUP_OK" in out.stdout, out.stdout[-3000:]
