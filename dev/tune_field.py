@@ -1,5 +1,5 @@
 """Sweep the field solver's scheduling knobs on one map (same bits expected everywhere).
-    python dev/tune_field.py [size]     env: MODES=0,1,2 TILES=0 DELTAS=128 INNERS=16 IDLES=1000 WAITS=200 SCHED=0 MERGE=0 FENCE=0 GATES=0"""
+    python dev/tune_field.py [size]     env: MODES=0,1,2,3,4 TILES=0 DELTAS=128 INNERS=16 IDLES=1000 WAITS=200 SCHED=0 MERGE=0 FENCE=0 GATES=0"""
 import sys, os, itertools
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'nav-stack-from-scratch_b200'))
@@ -15,7 +15,7 @@ while not fm[sj]: sj += 1
 src = (H // 2, sj)
 ev = lambda k, d: [int(x) for x in os.environ.get(k, d).split(',')]
 ref = None
-for mode, tiles, delta, inner, idle, wait, merge, fence, gate in itertools.product(ev('MODES', '0,1,2'), ev('TILES', '0'), ev('DELTAS', '128'), ev('INNERS', '16'),
+for mode, tiles, delta, inner, idle, wait, merge, fence, gate in itertools.product(ev('MODES', '0,1,2,3,4'), ev('TILES', '0'), ev('DELTAS', '128'), ev('INNERS', '16'),
                                                                            ev('IDLES', '1000'), ev('WAITS', '200'), ev('MERGE', '0'), ev('FENCE', '0'), ev('GATES', '0')):
     for k, v in (('field_mode', mode), ('field_tiles_per_sm', tiles), ('field_delta', delta), ('field_inner', inner), ('field_idle_ns', idle),
                  ('field_wait_ns', wait), ('field_merge', merge), ('field_fence', fence), ('field_gate', gate), ('field_sched_ns', int(os.environ.get('SCHED', '0')))):

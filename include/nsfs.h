@@ -247,7 +247,9 @@ long long   nsfs_kernel_launches(const nsfs_t* h);   /* kernels launched through
 void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the handle */
 /* Options (all have working defaults; 0 = default unless stated):
  *   "graph"          0 the reference's quirk graph | 1 textbook 8-connected grid; rebuilds the edge masks
- *   "field_mode"     warps per resident tile of the field solver: 0 = 4 (8 tiles resident per SM) | 1 = 8 (4 tiles) | 2 = 16 (2 tiles)
+ *   "field_mode"     warps per resident tile of the field solver: 0 = chosen from the map size | 1 = 4 warps (8 tiles resident per
+ *                    SM) | 2 = 8 (4 tiles) | 3 = 16 (2 tiles) | 4 = 32 (1 tile);  "field_gate"  how far (cost units) a block may run
+ *                    ahead of the slowest pending tile (0 = default for the residency, -1 = no gate)
  *   "field_tiles_per_sm"  cap on resident tiles per SM (0 = as many as fit)
  *   "field_delta", "field_inner", "field_idle_ns", "field_wait_ns", "field_sched_ns", "field_merge", "field_fence"
  *                    scheduling knobs of the field solver (band width in cost units, passes per sub-block turn, back-offs,

@@ -58,13 +58,17 @@ constexpr int NSB = SB_X * SB_Y;       // 128 sub-blocks per tile
 constexpr int SROW = TS + 8;           // smem row stride in words; SROW % 32 == 8 => the 4 rows of a sub-block use disjoint banks
 constexpr int SCOL0 = 4;               // smem column of tile column 0 (halo column -1 at 3)
 constexpr int SROWS = TS + 2;
+constexpr int kDummySlot = 0;          // s[0] (row 0, column 0: padding left of the halo column) always holds kInfQ: "no in-edge"
 
 // Which sub-blocks a warp owns.  Only the sub-blocks on the wavefront have work, so what counts is how many WARPS the
 // front's sub-blocks belong to.  warp = (sy + sx) mod WPT on the 16 x 8 grid of sub-blocks: the sides of the wave's octagon are
 // rows, columns and cell diagonals, i.e. sub-block lines (sy), (sx) and (sx, +-2 sx) (a sub-block is 8 wide, 4 tall); their
 // increments 1, 1, 1 +- 2 are all odd, so each such line is spread evenly over the WPT warps.
+// (32 warps: (sy + sx) only takes 23 values, so the lattice (2 sy + 5 sx) mod 32 of round 1 is used: rows, columns and both cell
+// diagonals of sub-blocks fall on distinct warps, two sub-blocks of one warp are >= 25 cells apart.)
 template <int WPT>
 __device__ __forceinline__ int sb_of(int warp, int slot) {           // (warp, slot) -> sub-block index sy * SB_X + sx
+    if (WPT == 32) { const int sx = 2 * slot + (warp & 1); return (((warp - 5 * sx) & 31) >> 1) * SB_X + sx; }
     if (WPT == 4) { const int sy = slot >> 1; return sy * SB_X + ((warp - sy) & 3) + 4 * (slot & 1); }
     if (WPT == 8) { return slot * SB_X + ((warp - slot) & 7); }
     return ((warp - slot) & 15) * SB_X + slot;                        // WPT == 16: slot = sx
@@ -73,6 +77,7 @@ template <int WPT>
 __device__ __forceinline__ int slot_of(int t) {                      // sub-block index -> index in s_due (warp-major)
     const int sy = t / SB_X, sx = t % SB_X;
     constexpr int SPW = NSB / WPT;
+    if (WPT == 32) return ((2 * sy + 5 * sx) & 31) * SPW + (sx >> 1);
     const int warp = (sy + sx) & (WPT - 1);
     if (WPT == 4) return warp * SPW + sy * 2 + (sx >> 2);
     if (WPT == 8) return warp * SPW + sy;
@@ -216,6 +221,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
         const int r = r0 + ly, c = c0 + lx;
         sm.mask[idx] = (r < H && c < W) ? __ldg(p.in_mask + (long long)r * W + c) : (uint16_t)0;
     }
+    if (tid == 0) sm.s[kDummySlot] = kInfQ;
     for (int t = tid; t < NSB; t += THREADS) sm.due[t] = key0;       // first pass: everything is due at the tile's own key
     if (tid < 16) sm.emin[tid] = kNoKey;
     if (tid < 4) sm.ctl[tid] = 0;
@@ -250,20 +256,26 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
             const int so = (ly + 1) * SROW + SCOL0 + lx;
             const uint32_t m = sm.mask[ly * TS + lx];
             uint32_t vq = s[so];
-            const volatile uint32_t* cc = s + so;
-            // edge weights of my cell: 1 or sqrt(2) in Q17.15, and an all-ones word ORed over candidates that have no in-edge
-            uint32_t wgt[8], off[8];
+            // Per direction, decided ONCE per turn and kept in registers: the weight (1 or sqrt(2) in Q17.15) and WHERE the candidate's
+            // source is read from: the neighbour's slot, or, for a direction without an in-edge, a dummy slot that holds kInfQ
+            // (kInfQ + weight never undercuts a cell).  A pass is then 8 shared loads, 8 adds, a min tree and one band test: the
+            // single warp that walks a sub-block issues dependent instructions ~5 cycles apart, so the pass's LENGTH in instructions
+            // is its latency (trace, round 2: 75 instructions and ~650 cycles per pass when the compiler re-derived the weights
+            // from the mask inside the loop).  The empty asm keeps the compiler from doing that again.
+            uint32_t wgt[8];
+            int src[8];
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 wgt[d] = ((m >> (8 + d)) & 1u) ? kQDiag : kQOne;
-                off[d] = ((m >> d) & 1u) ? 0u : 0xffffffffu;
+                src[d] = ((m >> d) & 1u) ? so - nb_di(d) * SROW - nb_dj(d) : kDummySlot;
+                asm volatile("" : "+r"(wgt[d]), "+r"(src[d]));
             }
             uint32_t bits = 0, last = 0, kchg = kNoKey;
             CYC_MARK(c_setup);
             for (int it = 0; it < p.inner; ++it) {
                 uint32_t cd[8];
 #pragma unroll
-                for (int d = 0; d < 8; ++d) cd[d] = (cc[-nb_di(d) * SROW - nb_dj(d)] + wgt[d]) | off[d];   // <= kInfQ + kQDiag: no wrap
+                for (int d = 0; d < 8; ++d) cd[d] = s[src[d]] + wgt[d];                                   // <= kInfQ + kQDiag: no wrap
                 // min as a tree (3 levels instead of a chain of 8); the band test on the minimum equals the test on every candidate
                 const uint32_t best = min(min(min(cd[0], cd[1]), min(cd[2], cd[3])), min(min(cd[4], cd[5]), min(cd[6], cd[7])));
                 const bool lower = best < vq;
@@ -513,7 +525,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
 // key + visits in flight; the kernel ends when it reaches zero.  Every spin loop has a bail-out (counts[4] bit 1) so the
 // kernel cannot hang.  Cooperative launch: blocks spin on each other's posts, so all of them must be resident.
 template <int WPT>
-__global__ void __launch_bounds__(WPT * 32, 32 / WPT) field_solve_async_kernel(FieldParams p) {
+__global__ void __launch_bounds__(WPT * 32, WPT == 32 ? 1 : 32 / WPT) field_solve_async_kernel(FieldParams p) {
     constexpr int THREADS = WPT * 32;
     __shared__ TileSmem<WPT> sm;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -756,7 +768,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.wait_ns = h->opt_field_wait_ns > 0 ? (unsigned)h->opt_field_wait_ns : 200u;
     p.cap = kNoKey - 1u;
     p.blk_key = f.blk_key; p.gfloor = f.blk_key + h->sm_count * 32 + 32;
-    p.gate = h->opt_field_gate > 0 ? to_q((double)h->opt_field_gate) : 0u;
+    p.gate = h->opt_field_gate > 0 ? to_q((double)h->opt_field_gate) : 0u;     // 0 = default for the residency chosen, < 0 = off
     return p;
 }
 
@@ -790,8 +802,8 @@ int launch_field_inject(nsfs_planner* h, int row0, int nrows, const float* d_val
     return NSFS_OK;
 }
 
-// The solve kernel for the handle's tile-residency setting: field_mode 0 = 4 warps per tile (8 tiles resident per SM),
-// 1 = 8 warps (4 tiles), 2 = 16 warps (2 tiles).  Same bits whichever runs.
+// The solve kernel for a tile-residency setting: field_mode 1 = 4 warps per tile (8 tiles resident per SM), 2 = 8 warps (4 tiles),
+// 3 = 16 warps (2 tiles), 4 = 32 warps (1 tile); 0 = chosen from the map size (launch_solve_any).  Same bits whichever runs.
 template <int WPT>
 static int launch_solve(nsfs_planner* h, FieldParams& p) {
     FieldWork& f = h->field;
@@ -837,10 +849,23 @@ static int launch_solve(nsfs_planner* h, FieldParams& p) {
     return NSFS_OK;
 }
 
-static int launch_solve_any(nsfs_planner* h, FieldParams& p) {
-    if (h->opt_field_mode == 1) return launch_solve<8>(h, p);
-    if (h->opt_field_mode == 2) return launch_solve<16>(h, p);
-    return launch_solve<4>(h, p);
+// Which residency?  Measured on one B200 (profiles/r02_field_solve.md): a map whose wavefront is never wider than the machine
+// (2048^2: <= ~130 tiles on the front for 148 SMs) is bound by how fast ONE visit crosses its tile, so it gets all 32 warps of
+// an SM per tile; a large map (16384^2: thousands of tiles on the front) is bound by visits per second, so it gets 4 resident
+// tiles of 8 warps per SM plus the global gate that keeps the extra concurrency from running ahead of the wave.
+static int launch_solve_any(nsfs_planner* h, FieldParams& p, bool allow_gate = true) {
+    long long mode = h->opt_field_mode;
+    if (mode <= 0) {
+        const long long n_tiles = (long long)p.tiles_x * p.tiles_y;
+        mode = n_tiles > 16ll * h->sm_count ? 2 : 4;
+        if (mode == 2 && h->opt_field_gate == 0) p.gate = to_q(192.0);
+        if (mode == 4 && h->opt_field_gate == 0) p.gate = 0u;
+    }
+    if (h->opt_field_gate < 0 || !allow_gate) p.gate = 0u;       // (the floor is per GPU: peer-to-peer shards gate nothing)
+    if (mode == 1) return launch_solve<4>(h, p);
+    if (mode == 2) return launch_solve<8>(h, p);
+    if (mode == 3) return launch_solve<16>(h, p);
+    return launch_solve<32>(h, p);
 }
 
 // Phase 3 (repeatable): relax every pending tile whose key is <= cap until none is left; nothing is relaxed beyond cap
@@ -871,9 +896,8 @@ int launch_field_relax_p2p(nsfs_planner* h) {
     if (f.own_hi > f.own_lo) { p.own_lo = f.own_lo; p.own_hi = f.own_hi; }
     p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
     p.merge = 0;
-    p.gate = 0;             // the floor is per GPU; shards gate nothing
     p.light = 0;            // peer posts need system scope: keep the fences
-    int rc = launch_solve_any(h, p);
+    int rc = launch_solve_any(h, p, false);
     if (rc != NSFS_OK) return rc;
     field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);
     h->launches++;

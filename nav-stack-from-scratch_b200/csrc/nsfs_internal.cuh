@@ -162,9 +162,9 @@ struct nsfs_planner {
     long long opt_field_inner = 0;      // 0 = default (16)
     long long opt_field_delta = 0;      // 0 = default (128)
     long long opt_graph = 0;            // 0 = the reference's quirk graph; 1 = textbook 8-connected grid
-    long long opt_field_mode = 0;       // warps per resident tile: 0 = 4 (8 tiles per SM), 1 = 8 (4 tiles), 2 = 16 (2 tiles)
+    long long opt_field_mode = 0;       // warps per resident tile: 0 = by map size, 1 = 4 (8 tiles per SM), 2 = 8 (4 tiles), 3 = 16 (2 tiles), 4 = 32 (1 tile)
     long long opt_field_tiles_per_sm = 0;   // cap on resident tiles per SM (0 = as many as fit)
-    long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = off)
+    long long opt_field_gate = 0;       // global gate on tile keys, cost units (0 = default for the residency, < 0 = off)
     long long opt_field_idle_ns = 0;    // 0 = default (1000)
     long long opt_field_fence = 0;      // 0 = __threadfence before key posts, 1 = release atomics (lighter fence, no L1 invalidate)
     long long opt_field_merge = 0;      // a visit absorbs posts that arrive for its own tile before it ends: 0 / 1 = on, 2 = off

@@ -220,8 +220,9 @@ def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
     P = gpu_lib.Planner(700, 900)
     P.set_map(infl, lo)
     want = P.field(src)
-    keys = ("field_mode", "field_tiles_per_sm", "field_delta", "field_inner", "field_merge", "field_fence", "field_idle_ns", "field_wait_ns")
-    for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_tiles_per_sm": 1}, {"field_mode": 1, "field_tiles_per_sm": 3},
+    keys = ("field_mode", "field_tiles_per_sm", "field_delta", "field_inner", "field_merge", "field_fence", "field_idle_ns", "field_wait_ns", "field_gate")
+    for opts in ({"field_mode": 1}, {"field_mode": 2}, {"field_mode": 3}, {"field_mode": 4}, {"field_tiles_per_sm": 1}, {"field_mode": 1, "field_tiles_per_sm": 3},
+                 {"field_mode": 1, "field_gate": 64}, {"field_mode": 2, "field_gate": 8}, {"field_mode": 3, "field_gate": 500}, {"field_gate": -1},
                  {"field_delta": 16}, {"field_delta": 100000}, {"field_delta": 3, "field_inner": 2}, {"field_inner": 1}, {"field_merge": 2},
                  {"field_fence": 1}, {"field_mode": 2, "field_merge": 2, "field_delta": 40}, {"field_idle_ns": 50, "field_wait_ns": 20}):
         for k in keys:

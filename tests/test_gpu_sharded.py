@@ -19,7 +19,7 @@ def _mono(gpu_lib, infl, lo, src):
 
 @pytest.mark.parametrize("spec", [(700, 520, 0.10, 51, True, 3), (260, 300, 0.22, 52, True, 4), (300, 130, 0.12, 53, False, 2)],
                          ids=["3-shards", "4-shards-dense", "2-shards-unframed-wrap"])
-@pytest.mark.parametrize("field_mode", [0, 2], ids=["8-tiles-per-sm", "2-tiles-per-sm"])
+@pytest.mark.parametrize("field_mode", [0, 1], ids=["residency-by-size", "8-tiles-per-sm"])
 def test_sharded_field_is_bit_identical_to_one_handle(gpu_lib, spec, field_mode, monkeypatch):
     monkeypatch.setenv("NSFS_FIELD_MODE", str(field_mode))       # read by nsfs_create: every handle below uses that solver
     H, W, p, seed, frame, world = spec
