@@ -15,6 +15,7 @@ Other workloads for single measurements (``--workload``):
   c3   ThetaStar, 4096x4096 raw map p=0.20 seed 9, the 16 sampler pairs run as one batch                [configs[2]]
   c5   Djikstra field on the 16384x16384 raw map p=0.10 seed 11 (N > 1: row blocks, p2p or NCCL rounds) [configs[4]]
   c4w  the C4 queries with 65 536 queries PER GPU (weak scaling; round-1 lines)
+  lat  single-query latency on the 2048x2048 map (north_star's latency target): the three ways a child serves ONE query
 
 A step = one pass of the hot path over one batch of synthetic input.  ``value`` is measured with inputs resident in HBM
 (device time of the step's kernels, CUDA events on the launching stream, L2 flushed between steps); ``e2e`` goes through
@@ -61,6 +62,8 @@ WORKLOADS = {
                name="Astar f single query, 384x384 inflated map p_occ=0.005 seed 1 (C1)"),
     "c3": dict(H=4096, W=4096, p=0.20, seed=9, inflated=False, algo="thetastar",
                name="ThetaStar f, 4096x4096 raw map p_occ=0.20 seed 9, the 16 sampler start/goal pairs as one batch (C3)"),
+    "lat": dict(H=2048, W=2048, p=0.10, seed=5, inflated=False, algo="djikstra",
+                name="single start/goal query latency on the 2048x2048 raw map p_occ=0.10 seed 5: Djikstra (field backend / exact order) and Astar f (exact order)"),
     "c5": dict(H=16384, W=16384, p=0.10, seed=11, inflated=False, algo="djikstra",
                name="Djikstra full cost-to-go field, 16384x16384 raw map p_occ=0.10 seed 11, source = centre (C5)"),
 }
@@ -353,6 +356,12 @@ def run_c5(torch, dist, rank, world, local, dev, steps, warmup, exchange="p2p", 
     shard = sf.FieldShard(part, rank, sf.GpuShardSolver(part, rank, infl, lo, device=local))
     P = shard.solver.P
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    group = None
+    if world > 1 and exchange == "p2p":
+        # the C-ABI group entry (NCCL bound inside libnsfs_gpu.so): CUDA IPC handles exchanged over NCCL, neighbours attached once
+        from nsfs import capi
+        group = capi.Group(dist, rank, world, local)
+        group.field_attach(P, shard.lo, shard.r0, shard.r1)
 
     def step():
         shard.solver.stats.clear()
@@ -361,7 +370,9 @@ def run_c5(torch, dist, rank, world, local, dev, steps, warmup, exchange="p2p", 
             return dict(reached=r["reached"], rounds=1, kernel_ms=r["stats"]["main_kernel_ms"], dev_ms=r["stats"]["gpu_ms"],
                         visits=r["stats"]["tile_visits"])
         if exchange == "p2p":
-            out = sf.solve_p2p(shard, src, dist, dev)
+            r = group.field_solve(P, src)              # seed, prime the shared counter, one solve kernel per GPU, finish
+            return dict(reached=r["stats"]["expansions"], rounds=1, kernel_ms=r["stats"]["main_kernel_ms"], dev_ms=r["stats"]["gpu_ms"],
+                        visits=r["stats"]["tile_visits"], status=r["status"])
         else:
             out = sf.solve_distributed(shard, src, dist, dev, band=band if band > 0 else None)
         return dict(reached=out["result"]["reached"], rounds=out["rounds"],
@@ -409,7 +420,7 @@ def run_c5(torch, dist, rank, world, local, dev, steps, warmup, exchange="p2p", 
         sp = sum(lv[4 + k] << (16 * k) for k in range(4)) % (1 << 64)
     out = dict(wall=wall, kernel_ms=kernel_ms, reached=reached, launches=launches, last=last, walls=walls, t_start=t_start,
                t_stop=t_stop, checksum_g=f"{sg:016x}", checksum_pred=f"{sp:016x}", steps=steps, H=H, W=W, P=P, shard=shard,
-               part=part, infl=infl, lo=lo, src=src)
+               part=part, infl=infl, lo=lo, src=src, group=group)
     want = None
     try:
         want = json.load(open(C5_CRC_FILE))
@@ -469,7 +480,7 @@ def c5_summary(r, world, exchange):
     d = {"workload": WORKLOADS["c5"]["name"], "gcell_relax_per_s": RELAX_PER_SETTLED * r["reached"] / r["wall"] / 1e9,
          "ms_per_field": 1e3 * r["wall"] / r["steps"], "p50_ms_per_field": 1e3 * float(np.median(r["walls"])), "steps": r["steps"],
          "partition": (f"{world} row blocks, 2 ghost rows of g + 4 rows of map per side, " +
-                       ("peer-to-peer posts over NVLink inside the solve kernel (no rounds)" if exchange == "p2p" else "NCCL rounds"))
+                       ("peer-to-peer posts over NVLink inside the solve kernel (no rounds), driven through nsfs_group_field_*" if exchange == "p2p" else "NCCL rounds"))
          if world > 1 else "single handle",
          "timing": "wall clock between cuda synchronize + barrier on both sides, max over ranks",
          "solve_kernel_ms_per_field_max_rank": r["kernel_ms"] / r["steps"], "roofline_frac": achieved / peak,
@@ -653,23 +664,21 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
     P.close()                                                      # the query slots (85 % of HBM) go back before the plugin-path leg
     del P
 
-    # ---- e2e: the reference-facing C++ child (GpuAstar::planBatch over the nsfsh_* shim), pageable MapData, results gathered ----
+    # ---- e2e: the reference-facing C++ child over the nsfsh_* shim.  N = 1: GpuAstar::planBatch.  N > 1: GpuAstar::planBatchSharded
+    # over a nsfs_host::DeviceGroup: rank 0 uploads its pageable MapData, the packed map is broadcast (NCCL, called from C++ below
+    # the C-ABI), every rank plans its slice and every rank gets all results back ----
     so, what = host_so()
-    host_q = np.ascontiguousarray(myq.cpu().numpy())
-    S = nhost.Session("astar", "f", infl, lo, device=local, so_path=so)
-    pad = -(-total // world)                                       # NCCL gather wants equal shares: pad the last rows
-    packed = torch.zeros((pad, 4), dtype=torch.float64, device=dev)
-    gathered = [torch.zeros((pad, 4), dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    all_host_q = np.ascontiguousarray(allq_t.cpu().numpy())
+    host_q = np.ascontiguousarray(all_host_q[a:b])
+    blank = np.zeros_like(infl)
+    S = nhost.Session("astar", "f", infl if rank == 0 else blank, lo if rank == 0 else blank, device=local, so_path=so)
+    cgroup = nhost.make_group(dist, rank, world, local, so_path=so) if world > 1 else None
 
     def step_e2e():
-        r = S.plan_batch_idx(host_q)                               # uploads both planes from pageable vectors, queries in, results out
-        if world > 1:                                              # result gather on rank 0 (NCCL), then to the host
-            packed[:nq].copy_(torch.from_numpy(np.stack([r["status"].astype(np.float64), r["g_goal"], r["path_len"].astype(np.float64),
-                                                    r["settled"].astype(np.float64)], 1)))
-            dist.gather(packed, gathered, dst=0)
-            if rank == 0:
-                torch.cat(gathered).cpu()
-        return r
+        if world > 1:
+            r = S.plan_batch_sharded(cgroup, all_host_q)
+            return {k: (v[a:b] if isinstance(v, np.ndarray) else v) for k, v in r.items()}
+        return S.plan_batch_idx(host_q)                            # uploads both planes from pageable vectors, queries in, results out
 
     e2e_steps = max(1, min(args.steps, 2))
     step_e2e()                                                     # allocates the session's own query slots
@@ -682,6 +691,8 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
     e2e_same = bool(np.array_equal(r_e2e["settled"], gpu_results["settled"]) and np.array_equal(r_e2e["g_goal"], gpu_results["g_goal"]))
+    if cgroup is not None:
+        nhost.destroy_group(cgroup, so_path=so)
     S.close()
     if world > 1:
         t = torch.tensor([e2e_sec, 0.0 if e2e_same else 1.0], dtype=torch.float64, device=dev)
@@ -701,6 +712,8 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
         try:
             r5 = run_c5(torch, dist, rank, world, local, dev, steps=3, warmup=2, exchange="p2p", want_e2e=False)
             extra_lines["c5"] = c5_summary(r5, world, "p2p")
+            if r5["group"] is not None:
+                r5["P"].field_peer_detach(); r5["group"].close()
             r5["shard"].solver.close()
         except Exception as e:          # noqa: BLE001
             extra_lines["c5"] = {"error": repr(e)}
@@ -721,10 +734,11 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": main_ms_max / args.steps,
                      "note": "per GPU: 9.125 B x the reference-settled cells of that rank's queries over its kernel time (max over ranks)"},
         "e2e": {"value": total * e2e_steps / e2e_sec, "unit": "queries/s",
-                "h2d_bytes_per_step": int(world * 2 * H * W * 4 + total * 16), "d2h_bytes_per_step": int(total * 24),
+                "h2d_bytes_per_step": int(2 * H * W * 4 + total * 16), "d2h_bytes_per_step": int(total * 24 * world),
                 "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps,
-                "path": f"{what}: GpuAstar::planBatch on a MapData with pageable std::vector<int> planes (uploaded every call), "
-                        "queries from host memory, per-query results back to the host" + (", then gathered on rank 0 over NCCL" if world > 1 else ""),
+                "path": f"{what}: " + ("GpuAstar::planBatch" if world == 1 else "GpuAstar::planBatchSharded over nsfs_host::DeviceGroup (map broadcast + "
+                        "result all-gather over NCCL, called from C++)") + " on a MapData with pageable std::vector<int> planes (uploaded every call), "
+                        "queries from host memory, per-query results back to the host",
                 "same_results_as_resident_path": e2e_same},
         "gpu_launches": launches_all,
         "clocks": sampler.finish() if sampler else None,
@@ -909,6 +923,50 @@ def ours_replicas(args, torch, dist, rank, world, local, dev):
     emit(line)
 
 
+def ours_latency(args, torch, local, dev):
+    """One query at a time on the 2048^2 map (north_star: "single-query latency below the CPU planner on 2048^2 grids"): the
+    plugin path (GpuDjikstra / GpuAstar::generatePath through the nsfsh_* shim, MapData uploaded once: on_notify) per planner."""
+    from nsfs import capi, host as nhost
+
+    wl = WORKLOADS["lat"]
+    H, W = wl["H"], wl["W"]
+    infl, lo = mapgen.synth_map(H, W, wl["p"], wl["seed"], False)
+    nq = max(4, min(args.steps, 16))
+    qs = mapgen.sample_queries(infl, lo, nq, wl["seed"])
+    so, what = host_so()
+    table = {}
+    for name, planner, mode, backend in (("djikstra_field_backend", "djikstra", "g", "field"), ("djikstra_exact_order", "djikstra", "g", "exact"),
+                                         ("astar_f_exact_order", "astar", "f", "exact")):
+        S = nhost.Session(planner, mode, infl, lo, backend=backend, device=local, so_path=so)
+        S.set_map_sync("on_notify")
+        S.generate_path_idx(qs[0][:2], qs[0][2:])
+        ms = []
+        for q in qs:
+            t0 = time.perf_counter(); S.generate_path_idx(q[:2], q[2:]); ms.append(1e3 * (time.perf_counter() - t0))
+        table[name] = {"p50_ms": float(np.median(ms)), "max_ms": float(np.max(ms))}
+        S.close()
+    line = {"metric": "single_query_p50_ms", "value": table["djikstra_field_backend"]["p50_ms"], "unit": "ms", "n_gpus": 1, "steps": nq, "warmup": 1,
+            "ms_per_step": table["djikstra_field_backend"]["p50_ms"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (Q17.15) / f64", "data": "synthetic", "config": shared_config("lat"),
+            "e2e": {"value": table["djikstra_field_backend"]["p50_ms"], "unit": "ms", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 8 * 4096,
+                    "path": f"{what}: generatePath, map resident (on_notify), wall clock per call"},
+            "gpu_launches": None, "extra": {"gpu": table, "queries": nq,
+                                            "note": "value = the Djikstra child with djikstra_backend: field (same reachability and cost as Djikstra::plan, "
+                                                    "an equal-cost path); the exact-order replays return the reference's identical path and are a serial chain"}}
+    if not args.no_cpu_baseline:
+        orc, impl, kind, have_ref = cpu_impl(infl, lo)
+        cpu = {}
+        for name, algo, mode in (("djikstra_g", 1, "g"), ("astar_f", 0, "f")):
+            ms = []
+            for q in qs:
+                t0 = time.perf_counter(); r = impl.plan(algo, mode, q[:2], q[2:]); dt = time.perf_counter() - t0
+                ms.append(1e3 * r.get("seconds", dt))
+            cpu[name] = {"p50_ms": float(np.median(ms)), "max_ms": float(np.max(ms))}
+        line["cpu_baseline"] = {"value": cpu["djikstra_g"]["p50_ms"], "unit": "ms", "cores": 1, "kind": kind, "table": cpu,
+                                "sample": f"the same {nq} queries, plan() one at a time on one core"}
+    emit(line)
+
+
 def ours(args):
     import torch
 
@@ -926,6 +984,9 @@ def ours(args):
             ours_c5(args, torch, dist, rank, world, local, dev)
         elif args.workload == "c4":
             ours_c4(args, torch, dist, rank, world, local, dev)
+        elif args.workload == "lat":
+            if rank == 0:
+                ours_latency(args, torch, local, dev)
         else:
             ours_replicas(args, torch, dist, rank, world, local, dev)
     finally:
@@ -950,7 +1011,7 @@ def main():
     args = ap.parse_args()
     # defaults that finish within minutes: a C4 step is seconds (65 536 queries), c2 3.5 ms, c1 ~0.1 s, c3 / c5 seconds
     if args.steps is None:
-        args.steps = {"c2": 30, "c1": 30}.get(args.workload, 2) if args.impl == "ours" else 2
+        args.steps = {"c2": 30, "c1": 30, "lat": 8}.get(args.workload, 2) if args.impl == "ours" else 2
     if args.warmup is None:
         args.warmup = {"c2": 5, "c1": 5}.get(args.workload, 3) if args.impl == "ours" else 1
     if args.warmup < 3 and args.impl == "ours":

@@ -646,7 +646,7 @@ int nsfs_field_peer_attach(nsfs_t* h, int side, const nsfs_peer_info* nb, int ro
     if ((rc = ipc_open(h, nb->g, &pg, 2 * side)) != NSFS_OK) return rc;
     if ((rc = ipc_open(h, nb->key, &pk, 2 * side + 1)) != NSFS_OK) return rc;
     h->field.peer_g[side] = (float*)pg; h->field.peer_key[side] = (uint32_t*)pk;
-    h->field.peer_row_off[side] = row_off; h->field.peer_tiles_y[side] = nb->tiles_y;
+    h->field.peer_row_off[side] = row_off; h->field.peer_tiles_y[side] = nb->tiles_y; h->field.peer_rows[side] = nb->rows;
     return NSFS_OK;
 }
 

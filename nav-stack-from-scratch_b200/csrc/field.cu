@@ -159,6 +159,38 @@ __global__ void __launch_bounds__(256) field_inject_kernel(FieldParams p, long l
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(improved, __popc(b));
 }
 
+// Peer-to-peer shards: before the solve kernel, whatever is already finite in my first / last two OWNED rows goes to the
+// neighbour's ghost rows.  The solve kernel only pushes cells that CHANGE in a visit, and the source (g = 0 from the seed, and
+// the cells a non-free source seeds) never does: a source in a shard's boundary rows would stay unknown to the neighbour, whose
+// cells next to it would then settle on a detour.  An improved ghost cell makes the neighbour's tiles that hold or read it
+// pending, exactly as field_inject_kernel does locally, and is added to the shared counter.
+__global__ void __launch_bounds__(256) field_push_boundary_kernel(FieldParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;            // 4 rows x W: rows own_lo, own_lo + 1 (side 0), own_hi - 2, own_hi - 1 (side 1)
+    if (t >= 4 * p.W) return;
+    const int which = t / p.W, c = t - which * p.W, side = which >> 1;
+    const int r = side == 0 ? p.own_lo + (which & 1) : p.own_hi - 2 + (which & 1);
+    if (!p.peer_g[side] || r < p.own_lo || r >= p.own_hi) return;
+    const uint32_t v = __ldcg(p.g + (long long)r * p.W + c);
+    if (v >= kInfQ) return;
+    const int rp = r + p.peer_row_off[side];                          // the neighbour's local row
+    const long long Np = (long long)p.peer_rows[side] * p.W, kp = (long long)rp * p.W + c;
+    if (rp < 0 || kp >= Np) return;
+    const uint32_t old = atomicMin(p.peer_g[side] + kp, v);
+    if (old <= v) return;
+    __threadfence_system();
+    int last = -1;
+#pragma unroll
+    for (int d = -1; d < 8; ++d) {
+        const long long kv = d < 0 ? kp : kp + nb_off(d, p.W);
+        if (kv < 0 || kv >= Np) continue;
+        const int tile = (int)(kv / p.W) / TS * p.tiles_x + (int)(kv % p.W) / TS;
+        if (tile == last) continue;
+        last = tile;
+        const uint32_t was = atomicMin(p.peer_key[side] + tile, v);
+        if (was == kNoKey) atomicAdd(p.gcount, 1);
+    }
+}
+
 // Key post with release semantics: orders this thread's earlier stores, and those of other threads it synchronised with
 // (__syncwarp / __syncthreads), before the key: MEMBAR.ALL.GPU + ATOMG, against MEMBAR.SC.GPU + CCTL.IVALL (an L1 invalidate)
 // + ATOMG for __threadfence() followed by a relaxed atomicMin.  Message passing needs no more than release / acquire.
@@ -758,7 +790,7 @@ static FieldParams field_params(nsfs_planner* h) {
     p.merge = h->opt_field_merge == 2 ? 0 : 1;
     p.sched_ns = h->opt_field_sched_ns > 0 ? (unsigned)h->opt_field_sched_ns : 400u;
     p.gcount = f.counts + 1;
-    for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; }
+    for (int sd = 0; sd < 2; ++sd) { p.peer_g[sd] = nullptr; p.peer_key[sd] = nullptr; p.peer_row_off[sd] = 0; p.peer_tiles_y[sd] = 0; p.peer_rows[sd] = 0; }
     p.own_lo = 0; p.own_hi = h->H;
     p.counts = f.counts; p.H = h->H; p.W = h->W; p.N = h->N; p.tiles_x = f.tiles_x; p.tiles_y = f.tiles_y;
     p.prof = nullptr;
@@ -891,12 +923,16 @@ int launch_field_relax_p2p(nsfs_planner* h) {
     FieldParams p = field_params(h);
     for (int sd = 0; sd < 2; ++sd) {
         p.peer_g[sd] = reinterpret_cast<uint32_t*>(f.peer_g[sd]); p.peer_key[sd] = f.peer_key[sd];
-        p.peer_row_off[sd] = f.peer_row_off[sd]; p.peer_tiles_y[sd] = f.peer_tiles_y[sd];
+        p.peer_row_off[sd] = f.peer_row_off[sd]; p.peer_tiles_y[sd] = f.peer_tiles_y[sd]; p.peer_rows[sd] = f.peer_rows[sd];
     }
     if (f.own_hi > f.own_lo) { p.own_lo = f.own_lo; p.own_hi = f.own_hi; }
     p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
     p.merge = 0;
     p.light = 0;            // peer posts need system scope: keep the fences
+    if (p.peer_g[0] || p.peer_g[1]) {
+        field_push_boundary_kernel<<<(4 * h->W + 255) / 256, 256, 0, h->stream>>>(p);
+        h->launches++;
+    }
     int rc = launch_solve_any(h, p, false);
     if (rc != NSFS_OK) return rc;
     field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);

@@ -64,6 +64,7 @@ struct FieldParams {
     uint32_t* peer_key[2];
     int peer_row_off[2];  // my local row r is the neighbour's local row r + peer_row_off[side]
     int peer_tiles_y[2];
+    int peer_rows[2];     // rows of the neighbour's plane
     int own_lo, own_hi;   // my owned local rows [own_lo, own_hi); the others are ghost rows (or inactive map rows)
     unsigned sched_ns;    // back-off of a block that owns no pending tile
     int merge;            // 1: a visit that is about to end first absorbs posts that arrived for its own tile meanwhile
@@ -89,6 +90,7 @@ struct FieldWork {
     uint32_t* peer_key[2] = {nullptr, nullptr};
     int       peer_row_off[2] = {0, 0};
     int       peer_tiles_y[2] = {0, 0};
+    int       peer_rows[2] = {0, 0};
     int*      peer_counts = nullptr;          // the counter owner's counts array (nullptr: mine)
     void*     ipc_opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int       own_lo = 0, own_hi = 0;         // owned local rows (0, 0 = all)

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
     long long pops = 0, expansions = 0, pushes = 0;
 
     for (;;) {
-        // ---- next query -----------------------------------------------------------------------------------------
-        {
+        // ---- next query (skipped by the whole warp unless one of its four teams wants one) ---------------------------
+        if (__any_sync(FULL, phase == PH_FETCH)) {
             const bool fetch = phase == PH_FETCH;
             int q = 0;
             if (fetch && tl == 0) q = atomicAdd(p.work_counter, 1);
@@ -234,11 +234,6 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 if (tl == 0) cu_l = __ldcg(cells + ku);
                 if (tl == 1) om_l = __ldg(p.out_mask + ku);
             }
-            if (act && tl >= 1 && n > kTopN) {
-                // the first push after this pop rises from position n (= n_after_pop + 1): start its ancestors on their way
-                const uint32_t q = n >> tl;
-                if (q >= kTopN) asm volatile("prefetch.global.L1 [%0];" :: "l"(heap.a + q));
-            }
             team_pop<MODE>(heap, n, act, tl, tbase, nr, no);
             uint2 cu;
             cu.x = __shfl_sync(FULL, cu_l.x, 0, 8); cu.y = __shfl_sync(FULL, cu_l.y, 0, 8);
@@ -261,23 +256,41 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 const bool valid = (pre.y >> 4) == epoch;
                 const bool diag = ((om >> (8 + tl)) & 1u) && tl;
                 const uint32_t nc = (cu.x & 0xffffu) + (diag ? 0u : 1u), nd = (cu.x >> 16) + (diag ? 1u : 0u);
-                const double cand = __dadd_rn((double)nc, __dmul_rn((double)nd, kSqrt2D));
-                const double gv = valid ? __dadd_rn((double)(pre.x & 0xffffu), __dmul_rn((double)(pre.x >> 16), kSqrt2D)) : kInfD;
-                relax = gv > __dadd_rn(cand, kSlack);                                                      // astar.cpp:116
+                // astar.cpp:116  g[v] > cand + 1e-5  on labels a + b*sqrt(2) held as exact step counts: with da = a_v - a, db = b_v - b the
+                // difference da + db*sqrt(2) is 0 or at least 1 / (|da| + |db| sqrt(2)) > 1e-5 away from 0 (|da| < 2^16, |db| < 2^14), so the
+                // test is the SIGN of da + db*sqrt(2): decided by the signs, or by da^2 against 2 db^2 when they differ.  Integers only.
+                if (!valid) relax = true;
+                else {
+                    const int da = (int)(pre.x & 0xffffu) - (int)nc, db = (int)(pre.x >> 16) - (int)nd;
+                    if (db > -16384 && db < 16384) {
+                        if (db == 0) relax = da > 0;
+                        else if (da == 0) relax = db > 0;
+                        else if ((da ^ db) >= 0) relax = da > 0;
+                        else {
+                            const unsigned long long a2 = (unsigned long long)((long long)da * da), b2 = 2ull * (unsigned long long)((long long)db * db);
+                            relax = da > 0 ? a2 > b2 : b2 > a2;
+                        }
+                    } else {
+                        const double cand = __dadd_rn((double)nc, __dmul_rn((double)nd, kSqrt2D));
+                        const double gv = __dadd_rn((double)(pre.x & 0xffffu), __dmul_rn((double)(pre.x >> 16), kSqrt2D));
+                        relax = gv > __dadd_rn(cand, kSlack);
+                    }
+                }
                 if (relax) {
                     if (nc > 0xffffu || nd > 0xffffu) { overflow = true; relax = false; }
                     else {
                         __stcg(cells + kv, make_uint2(nc | (nd << 16), (epoch << 4) | (valid ? (pre.y & 8u) : 0u) | (uint32_t)tl));
-                        double f = 0.0;
+                        // keys (grid_planner_core.cpp:385-391): (int)g = a + floor(b sqrt 2); (int)(g + h) with h = ord*sqrt(2) + card (dist_oct
+                        // with the row slip, bot_utils.cpp:44-65) = a + card + floor((b + ord) sqrt 2).  k*sqrt(2) stays >= 1 / (2.83 k) away
+                        // from every integer and one fp64 product is good to 1e-16 relative, so the truncations are the reference's.
+                        const uint32_t gi32 = nc + (uint32_t)__double2int_rz(__dmul_rn((double)nd, kSqrt2D));
+                        uint32_t fi = 0u;
                         if (mode != NSFS_MODE_G) {
-                            double h = 0.0;
                             if (ALGO == NSFS_ASTAR) {
                                 const int ax = abs(gi - vi), ay = abs(gj - vi);
-                                h = __dadd_rn(__dmul_rn((double)min(ax, ay), kSqrt2D), (double)abs(ax - ay));
-                            }
-                            f = __dadd_rn(cand, h);
+                                fi = nc + (uint32_t)abs(ax - ay) + (uint32_t)__double2int_rz(__dmul_rn((double)(nd + (uint32_t)min(ax, ay)), kSqrt2D));
+                            } else fi = gi32;
                         }
-                        const uint32_t fi = (uint32_t)__double2int_rz(f), gi32 = (uint32_t)__double2int_rz(cand);
                         if (fi > 0xffffu || gi32 > 0xffffu) { overflow = true; relax = false; }     // (the record is written; the query is abandoned anyway)
                         entry = ((unsigned long long)((fi << 16) | (gi32 & 0xffffu)) << 32) | (unsigned long long)kv;
                     }
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
         }
 
         // ---- one step of the back-track for every team that found its goal (astar.cpp:70-82) ---------------------------
-        {
+        if (__any_sync(FULL, phase == PH_WALK)) {
             const bool walking = phase == PH_WALK;
             uint32_t nk = 0;
             if (walking && tl == 0) {

@@ -47,6 +47,9 @@ for (H, W, p, seed) in [(512, 384, 0.10, 71), (640, 200, 0.2, 73), (1024, 1536, 
     infl, lo = mapgen.synth_map(H, W, p, seed)
     src = tuple(int(x) for x in mapgen.sample_free_cells(infl, lo, 1, seed)[0])
     part = sf.RowPartition(H, W, world)
+    if seed == 73:                                    # the source in the last owned row of rank 0 (see tests/p2p_worker.py)
+        row = part.bounds[1] - 1
+        src = (row, int(np.nonzero(mapgen.free_mask(infl, lo)[row])[0][5]))
     shard = sf.make_gpu_shard(part, rank, infl, lo, device=local)
     Ps = shard.solver.P
     G.field_attach(Ps, shard.lo, shard.r0, shard.r1)
