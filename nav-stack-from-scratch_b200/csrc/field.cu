@@ -415,8 +415,11 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
                     // Before ending the visit: did a neighbour post to THIS tile meanwhile (within the band)?  Then stay on it:
                     // take the key, re-read the halo ring, wake the sub-blocks next to halo cells that dropped.  Saves the
                     // publish / claim / stage round trip of a separate visit, which sits on the wavefront's critical path.
+                    // (Not for a tile that sticks out over the map's right edge: the staged positions beyond column W-1 mirror cells of
+                    // the NEXT row's first columns - the flat-key wrap - and sit inside the square, not on the ring that is re-read
+                    // here; round 2 found such a tile keeping a stale mirror on an unframed 300x130 map.  Those tiles end and are staged afresh.)
                     uint32_t pk = kNoKey;
-                    if (p.merge) {
+                    if (p.merge && c0 + TS <= W) {
                         if (lane == 0) {
                             pk = __ldcg(p.tile_key + tile);
                             pk = (pk <= thr && pk <= p.cap) ? atomicExch(p.tile_key + tile, kNoKey) : kNoKey;

@@ -34,6 +34,12 @@ for (H, W, p, seed, frame) in [(512, 384, 0.10, 71, True), (256, 192, 0.12, 72, 
         G = np.concatenate([x[0] for x in parts]); PR = np.concatenate([x[1] for x in parts])
         same = np.array_equal(G, want["g"]) and np.array_equal(PR, want["pred"]) and sum(x[2] for x in parts) == want["reached"]
         ok = ok and same
+        if not same:
+            bad = np.argwhere(G != want["g"])
+            print(f"  g differs in {len(bad)} cells, rows {bad[:, 0].min() if len(bad) else -1}..{bad[:, 0].max() if len(bad) else -1}, cols "
+                  f"{bad[:, 1].min() if len(bad) else -1}..{bad[:, 1].max() if len(bad) else -1}; shard bounds {part.bounds}; src {src}; first: "
+                  + ", ".join(f"({r},{c}) got {G[r, c]:.4f} want {want['g'][r, c]:.4f}" for r, c in bad[:6])
+                  + f"; pred differs in {(PR != want['pred']).sum()}; reached {sum(x[2] for x in parts)} vs {want['reached']}", flush=True)
         print(f"{H}x{W} world {world}: identical={same} statuses={[x[3] for x in parts]} wall {dt*1e3:.2f} ms kernel_ms {[round(x[4],2) for x in parts]} single {want['stats']['main_kernel_ms']:.2f} ms", flush=True)
     shard.solver.P.field_peer_detach(); shard.solver.close()
     dist.barrier()

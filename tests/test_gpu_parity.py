@@ -211,6 +211,34 @@ def test_fallback_in_shared_memory_agrees_with_the_wide_kernel(gpu_lib, oracle_m
 
 
 @pytest.mark.gpu
+def test_ragged_right_edge_tiles_of_an_unframed_map(gpu_lib, oracle_mod):
+    """Unframed map whose width is no multiple of the 64-cell tile: the last tile column's staged square holds, beyond column
+    W-1, mirrors of the next row's first cells (the reference's flat-key wrap, grid_planner_core.cpp:423-426).  A visit that
+    stayed resident and only re-read its halo ring kept those mirrors stale (found by the 2-GPU run of round 2, where the
+    single-handle field came out 3 - 2*sqrt(2) too high in 38 cells).  Every residency, repeated, against the CPU planner."""
+    H, W = 300, 130
+    infl, lo = mapgen.synth_map(H, W, 0.12, 74, False, False)
+    for c in ((0, 0), (1, 0), (H - 1, W - 1), (H - 2, W - 1)):
+        infl[c] = 1; lo[c] = 20
+    src = (254, 81)
+    o = oracle_mod.Oracle(infl, lo).field(src)
+    reach = o["g"] < 1e5
+    P = gpu_lib.Planner(H, W)
+    P.set_map(infl, lo)
+    first = None
+    for rep in range(6):
+        for mode in (0, 1, 2, 3, 4):
+            P.set_option("field_mode", mode)
+            r = P.field(src)
+            assert r["status"] == 0 and np.array_equal(r["g"] < 1e5, reach)
+            rel = np.abs(r["g"].astype(np.float64) - o["g"])[reach] / np.maximum(o["g"][reach], 1.0)
+            assert rel.max() <= 1e-5, (rep, mode, rel.max())
+            first = r if first is None else first
+            assert np.array_equal(r["g"], first["g"]) and np.array_equal(r["pred"], first["pred"]), (rep, mode)
+    P.close()
+
+
+@pytest.mark.gpu
 def test_every_field_scheduler_returns_the_same_bits(gpu_lib):
     """The field is solved in exact integer arithmetic (Q17.15), so its fixed point cannot depend on the schedule: every
     tile-residency setting (4 / 8 / 16 warps per resident tile, fewer resident tiles per SM), band width, pass budget, fence
