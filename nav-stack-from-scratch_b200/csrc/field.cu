@@ -896,7 +896,7 @@ static int launch_solve_any(nsfs_planner* h, FieldParams& p, bool allow_gate = t
         if (mode == 2 && h->opt_field_gate == 0) p.gate = to_q(192.0);
         if (mode == 4 && h->opt_field_gate == 0) p.gate = 0u;
     }
-    if (h->opt_field_gate < 0 || !allow_gate) p.gate = 0u;       // (the floor is per GPU: peer-to-peer shards gate nothing)
+    if (h->opt_field_gate < 0 || !allow_gate) p.gate = 0u;
     if (mode == 1) return launch_solve<4>(h, p);
     if (mode == 2) return launch_solve<8>(h, p);
     if (mode == 3) return launch_solve<16>(h, p);
@@ -936,7 +936,9 @@ int launch_field_relax_p2p(nsfs_planner* h) {
         field_push_boundary_kernel<<<(4 * h->W + 255) / 256, 256, 0, h->stream>>>(p);
         h->launches++;
     }
-    int rc = launch_solve_any(h, p, false);
+    // The gate's floor is this GPU's own smallest key: the block that holds it is always eligible, posts from the neighbour
+    // shards lower keys (and with them the floor) like local ones, so gating each shard on its own floor cannot stall the group.
+    int rc = launch_solve_any(h, p, true);
     if (rc != NSFS_OK) return rc;
     field_pending_kernel<<<1, 256, 0, h->stream>>>(f.tile_key, f.tiles_x * f.tiles_y, p.cap, f.counts, 1);
     h->launches++;

@@ -73,14 +73,18 @@ __device__ __forceinline__ uint32_t prio_of(unsigned long long e) {
 
 __device__ __forceinline__ unsigned team_ballot(bool pred, int tbase) { return (__ballot_sync(FULL, pred) >> tbase) & 0xffu; }
 
-// One open list: positions < kTopN in shared memory (s), the rest in global memory (a); position = heap index + 1.
+// One open list: positions < kTopN in shared memory, the rest in global memory; position = heap index + 1.  Both halves are
+// reached through ONE generic pointer chosen with a select (no branch): the first version of this split branched per access and
+// its extra ~80 instructions per pop cost more than the saved round trips (ncu, round 2: the accessors were 20 % of all
+// instructions and the kernel is bound by how many it issues in sequence, not by memory).
 struct TeamHeap {
-    unsigned long long* a;
-    unsigned long long* s;
-    __device__ __forceinline__ unsigned long long ld(uint32_t pos) const { return pos < kTopN ? s[pos] : a[pos]; }
-    __device__ __forceinline__ void st(uint32_t pos, unsigned long long v) const { if (pos < kTopN) s[pos] = v; else a[pos] = v; }
+    unsigned long long* a;        // global part (whole array; positions < kTopN unused)
+    unsigned long long* s;        // generic pointer to this team's shared-memory top
+    __device__ __forceinline__ unsigned long long* at(uint32_t pos) const { return (pos < kTopN ? s : a) + pos; }
+    __device__ __forceinline__ unsigned long long ld(uint32_t pos) const { return *at(pos); }
+    __device__ __forceinline__ void st(uint32_t pos, unsigned long long v) const { *at(pos) = v; }
     __device__ __forceinline__ ulonglong2 ld_pair(uint32_t lpos) const {     // lpos even: both children on the same side of kTopN
-        return lpos < kTopN ? *reinterpret_cast<const ulonglong2*>(s + lpos) : *reinterpret_cast<const ulonglong2*>(a + lpos);
+        return *reinterpret_cast<const ulonglong2*>(at(lpos));
     }
 };
 
@@ -107,17 +111,16 @@ __device__ __forceinline__ void team_pop(const TeamHeap hp, uint32_t& n, bool ac
         const bool stop = !has || prio_of<MODE>(pick) > pv;
         const unsigned m_left = team_ballot(left, tbase);
         const unsigned m_stop = team_ballot(stop, tbase);
-        uint32_t node = 0, steps = 0, path = 0;
-#pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {
-            if ((m_stop >> node) & 1u) break;
-            path |= 1u << node;
-            node = 2u * node + 2u - ((m_left >> node) & 1u);
-            ++steps;
-        }
+        // the path through the three levels, straight-line (the same chain of three bit tests as a loop, without its branches);
+        // o1..o3 = offset of the path's node within its level, so the hole's new position needs no clz
+        const uint32_t l0 = m_left & 1u, o1 = 1u - l0, n1 = 1u + o1;
+        const uint32_t l1 = (m_left >> n1) & 1u, o2 = 2u * o1 + 1u - l1, n2 = 3u + o2;
+        const uint32_t l2 = (m_left >> n2) & 1u, o3 = 2u * o2 + 1u - l2;
+        const bool s0 = m_stop & 1u, s1 = (m_stop >> n1) & 1u, s2 = (m_stop >> n2) & 1u;
+        const uint32_t steps = s0 ? 0u : (s1 ? 1u : (s2 ? 2u : 3u));
+        const uint32_t path = s0 ? 0u : (1u | (s1 ? 0u : ((1u << n1) | (s2 ? 0u : (1u << n2)))));
+        const uint32_t npos = s0 ? c1 : (s1 ? 2u * c1 + o1 : (s2 ? 4u * c1 + o2 : 8u * c1 + o3));
         if (sinking && ((path >> tl) & 1u)) hp.st(pos, pick);
-        const int rq = 31 - __clz(node + 1u);
-        const uint32_t npos = (c1 << rq) + (node + 1u - (1u << rq));
         if (sinking) {
             if (steps < 3u) { if (tl == 0) hp.st(npos, v); sinking = false; }
             else c1 = npos;
