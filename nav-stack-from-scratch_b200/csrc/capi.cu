@@ -104,6 +104,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
     if (const char* e = getenv("NSFS_FIELD_FENCE")) h->opt_field_fence = atoi(e);
     if (const char* e = getenv("NSFS_SEARCH_ORDER")) h->opt_search_order = atoi(e);
     if (const char* e = getenv("NSFS_MAX_SLOTS")) h->opt_max_slots = atoll(e);    // warps of query slots (experiments)
+    if (const char* e = getenv("NSFS_FIELD_GATE")) h->opt_field_gate = atoi(e);
     if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
     *out = h;
     return NSFS_OK;

@@ -200,6 +200,24 @@ __device__ __forceinline__ uint32_t atomic_min_release(uint32_t* addr, uint32_t 
     return old;
 }
 
+// Wake the neighbour shard's tiles that hold, or read as halo, the two boundary rows this shard pushes: its rows R-3 .. R+4 lie in
+// at most two tile rows; columns tx-1 .. tx+1 plus the far edge column when this tile touches a map edge (flat-key wrap).
+// slot 0..7 = (tile row, column choice); returns 1 if the post made a tile pending.
+template <int WPT>
+__device__ __forceinline__ int peer_post(const FieldParams& p, int side, int slot, int tx, uint32_t m) {
+    if (!p.peer_key[side] || m == kNoKey) return 0;
+    const int R = (side == 0 ? p.own_lo : p.own_hi - 2) + p.peer_row_off[side];      // first pushed row, neighbour-local
+    const int tr0 = max(R - 3, 0) / TS, tr1 = min(R + 4, p.peer_tiles_y[side] * TS - 1) / TS;
+    const int trow = (slot & 1) ? tr1 : tr0;
+    const int cs = slot >> 1;                                      // 0..2: tx-1..tx+1, 3: the wrap column
+    const int tcol = cs < 3 ? tx + cs - 1 : (tx == 0 ? p.tiles_x - 1 : (tx == p.tiles_x - 1 ? 0 : -1));
+    bool dup = ((slot & 1) && tr1 == tr0) || tcol < 0 || tcol >= p.tiles_x;
+    if (cs == 3 && !dup) dup = abs(tcol - tx) <= 1;                // already covered by the three neighbour columns
+    if (dup) return 0;
+    const uint32_t old = atomicMin(p.peer_key[side] + trow * p.tiles_x + tcol, m);
+    return (old > p.cap && m <= p.cap) ? 1 : 0;
+}
+
 template <int WPT>
 struct __align__(16) TileSmem {
     uint32_t s[SROWS * SROW];      // the tile and its halo: position (rr, cc) holds g[(r0-1+rr)*W + (c0-1+cc)] (flat key!)
@@ -345,6 +363,7 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
                 // ---- write the cells that changed back to L2 --------------------------------------------------------
                 const int r = r0 + ly, c = c0 + lx;
                 const bool mine = (bits >> lane) & 1u;
+                unsigned pushed = 0;                                  // bit side: my cell went to that neighbour shard
                 if (mine && r < H && c < W) {
                     const long long gk = (long long)r * W + c;
                     if (peers && (r < p.own_lo || r >= p.own_hi)) {
@@ -354,14 +373,8 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
                         __stcg(p.g + gk, vq);
                         if (peers) {
                             // my first / last two owned rows ARE the neighbour's ghost rows: push the value over NVLink
-                            if (p.peer_g[0] && r < p.own_lo + 2) {
-                                atomicMin(p.peer_g[0] + (long long)(r + p.peer_row_off[0]) * W + c, vq);
-                                atomicMin(sm.emin + 12, vq);
-                            }
-                            if (p.peer_g[1] && r >= p.own_hi - 2) {
-                                atomicMin(p.peer_g[1] + (long long)(r + p.peer_row_off[1]) * W + c, vq);
-                                atomicMin(sm.emin + 13, vq);
-                            }
+                            if (p.peer_g[0] && r < p.own_lo + 2) { atomicMin(p.peer_g[0] + (long long)(r + p.peer_row_off[0]) * W + c, vq); pushed = 1; }
+                            if (p.peer_g[1] && r >= p.own_hi - 2) { atomicMin(p.peer_g[1] + (long long)(r + p.peer_row_off[1]) * W + c, vq); pushed |= 2; }
                         }
                     }
                     // flat-key wrap at the map's column edges: (r, W-1) feeds (r..r+2, 0), (r, 0) feeds (r-2..r, W-1); posted at the visit's end
@@ -370,6 +383,24 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
                 }
                 // ---- cut-through between tiles: a changed cell that faces another tile is announced NOW (value, fence, key),
                 // so the neighbouring tile starts on the wavefront while this one is still relaxing
+                if (peers) {
+                    // cut-through ACROSS GPUs: rows pushed in this turn are announced to the neighbour shard now (system-scope fence,
+                    // then remote key posts), like the local posts below; only tiles on a shard boundary ever get here.  Waiting for the
+                    // visit's end made every exchange across the boundary cost a whole visit, and a source on the boundary (16384 rows
+                    // over an even number of ranks) sends the main wave ALONG it.
+                    const unsigned pm = __reduce_or_sync(0xffffffffu, pushed);
+                    if (pm) {
+                        __threadfence_system();
+                        __syncwarp();
+                        if (lane < 16) {
+                            const int side = lane >> 3;
+                            if ((pm >> side) & 1u) {
+                                const int add = peer_post<WPT>(p, side, lane & 7, tx, kmin);
+                                if (add) atomicAdd(p.gcount, add);
+                            }
+                        }
+                    }
+                }
                 CYC_MARK(c_wb);
                 uint32_t outer = 0;
                 if (sby == 0) outer |= bits & 0x000000ffu;
@@ -454,6 +485,27 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
                                     }
                             }
                         }
+                        if (peers && (r0 < p.own_lo || r0 + TS > p.own_hi)) {
+                            // a shard's tile that holds ghost rows: the neighbour lowers those cells remotely INSIDE the square, so they are
+                            // re-read as well (rows of the tile outside my owned range; at most a few)
+                            for (int ly2 = 0; ly2 < TS; ++ly2) {
+                                const int r2 = r0 + ly2;
+                                if ((r2 >= p.own_lo && r2 < p.own_hi) || r2 >= H) continue;
+                                for (int lx2 = lane; lx2 < TS; lx2 += 32) {
+                                    if (c0 + lx2 >= W) continue;
+                                    const uint32_t nv = __ldcg(p.g + (long long)r2 * W + c0 + lx2);
+                                    const int so2 = (ly2 + 1) * SROW + SCOL0 + lx2;
+                                    if (nv < s[so2]) {
+                                        s[so2] = nv;
+                                        // the cell's own sub-block and the ones within one step of it
+                                        const int y0 = max(ly2 - 1, 0), y1 = min(ly2 + 1, TS - 1), x0 = max(lx2 - 1, 0), x1 = min(lx2 + 1, TS - 1);
+                                        for (int yy = 0; yy < 2; ++yy)
+                                            for (int xx = 0; xx < 2; ++xx)
+                                                atomicMin(sm.due + slot_of<WPT>(((yy ? y1 : y0) / SBH) * SB_X + (xx ? x1 : x0) / SBW), nv);
+                                    }
+                                }
+                            }
+                        }
                         __syncwarp();
                         continue;                                     // poll again: my own sub-blocks may be due; idle + finisher check come after
                     }
@@ -482,30 +534,8 @@ __device__ __forceinline__ void relax_tile(const FieldParams& p, int tile, uint3
     __syncthreads();
     // Every changed cell was stored during the visit; the keys posted from here on announce values whose stores a block
     // barrier has ordered before this point, and a fence is cumulative over what happened before it.
-    if (tid < 32) {
-        if (peers) __threadfence_system();                            // ... also on the neighbour GPU
-        else if (!p.light) __threadfence();
-    }
+    if (tid < 32 && !p.light) __threadfence();       // (rows pushed to a neighbour shard were fenced and announced in the turn that pushed them)
     int newly = 0;        // tiles this thread made pending: summed over warp 0 and folded into ONE update of the pending counter
-    if (tid >= 16 && tid < 32) {
-        // wake the neighbour shard's tiles that hold, or read as halo, the two rows pushed during the visit: its rows R-3 .. R+4 lie
-        // in at most two tile rows; columns tx-1 .. tx+1 plus the far edge column when this tile touches a map edge (flat-key wrap)
-        const int side = (tid - 16) >> 3, slot = (tid - 16) & 7;
-        const uint32_t m = sm.emin[12 + side];
-        if (p.peer_key[side] && m != kNoKey) {
-            const int R = (side == 0 ? p.own_lo : p.own_hi - 2) + p.peer_row_off[side];      // first pushed row, neighbour-local
-            const int tr0 = max(R - 3, 0) / TS, tr1 = min(R + 4, p.peer_tiles_y[side] * TS - 1) / TS;
-            const int trow = (slot & 1) ? tr1 : tr0;
-            const int cs = slot >> 1;                                      // 0..2: tx-1..tx+1, 3: the wrap column
-            int tcol = cs < 3 ? tx + cs - 1 : (tx == 0 ? p.tiles_x - 1 : (tx == p.tiles_x - 1 ? 0 : -1));
-            bool dup = ((slot & 1) && tr1 == tr0) || tcol < 0 || tcol >= p.tiles_x;
-            if (cs == 3 && !dup) dup = abs(tcol - tx) <= 1;                // already covered by the three neighbour columns
-            if (!dup) {
-                const uint32_t old = atomicMin(p.peer_key[side] + trow * p.tiles_x + tcol, m);
-                if (old > p.cap && m <= p.cap) newly = 1;
-            }
-        }
-    }
     {
         // key posts: 9..11 right map edge -> left-edge tiles of tile rows ty-1..ty+1, 12..14 left map edge -> right-edge tiles
         // of rows ty-1..ty+1, 15 this tile's own rejected candidates.  (The 8 direct neighbours were posted during the visit.)
@@ -580,7 +610,14 @@ __global__ void __launch_bounds__(WPT * 32, WPT == 32 ? 1 : 32 / WPT) field_solv
             m = __reduce_min_sync(0xffffffffu, m);
             if (lane == 0) atomicMin(&sm.key, m);
             __syncthreads();
-            if (tid == 0) { __stcg(p.gfloor, sm.key); sm.emin[0] = (uint32_t)atomicAdd(p.gcount, 0); }
+            if (tid == 0) {
+                __stcg(p.gfloor, sm.key);
+                const int pend = atomicAdd(p.gcount, 0);
+                sm.emin[0] = (uint32_t)pend;
+                // the workers read the pending count HERE (0 = not published yet), not from the counter itself: with shards the
+                // counter lives on another GPU, and hundreds of idle blocks polling it over NVLink would crowd out the real posts
+                __stcg(p.gfloor + 1, (uint32_t)(pend > 0 ? pend : 0) + 1u);
+            }
             __syncthreads();
             const int pending = (int)sm.emin[0];
             __syncthreads();
@@ -605,7 +642,11 @@ __global__ void __launch_bounds__(WPT * 32, WPT == 32 ? 1 : 32 / WPT) field_solv
         if (gated && tid == 0) __stcg(p.blk_key + blockIdx.x, pick == ~0ull ? kNoKey : (uint32_t)(pick >> 32));
         if (pick == ~0ull) {
             int pending = 1;
-            if (tid == 0) { pending = atomicAdd(p.gcount, 0); sm.key = (uint32_t)pending; }
+            if (tid == 0) {
+                const uint32_t pub = gated ? __ldcg(p.gfloor + 1) : 0u;
+                pending = pub ? (int)pub - 1 : atomicAdd(p.gcount, 0);
+                sm.key = (uint32_t)pending;
+            }
             __syncthreads();
             pending = (int)sm.key;
             __syncthreads();
@@ -930,7 +971,6 @@ int launch_field_relax_p2p(nsfs_planner* h) {
     }
     if (f.own_hi > f.own_lo) { p.own_lo = f.own_lo; p.own_hi = f.own_hi; }
     p.gcount = (f.peer_counts ? f.peer_counts : f.counts) + 1;
-    p.merge = 0;
     p.light = 0;            // peer posts need system scope: keep the fences
     if (p.peer_g[0] || p.peer_g[1]) {
         field_push_boundary_kernel<<<(4 * h->W + 255) / 256, 256, 0, h->stream>>>(p);
