@@ -626,47 +626,49 @@ __global__ void __launch_bounds__(WPT * 32, WPT == 32 ? 1 : 32 / WPT) field_solv
         }
         return;
     }
+    // Picking the next tile is WARP 0's job; the other warps of the block wait at the barrier, where they issue nothing.  (Round 2,
+    // ncu on C2: with every warp of every idle or gated block running this scan and its shuffles every 400 ns, the scan was 25 % of
+    // all instructions executed; with several blocks resident per SM it competed with the visits next door for issue slots.)
+    const int warp_id = tid >> 5;
     int idle_spins = 0;
     for (long long iter = 0; iter < (1ll << 40); ++iter) {
-        if (tid == 0) sm.best = ~0ull;
-        __syncthreads();
-        unsigned long long best = ~0ull;
-        for (int t = blockIdx.x + tid * workers; t < n_tiles; t += workers * THREADS) {
-            const uint32_t k = __ldcg(p.tile_key + t);
-            if (k <= p.cap) best = min(best, ((unsigned long long)k << 32) | (unsigned)t);
+        if (warp_id == 0) {
+            unsigned long long best = ~0ull;
+            for (int t = blockIdx.x + lane * workers; t < n_tiles; t += workers * 32) {
+                const uint32_t k = __ldcg(p.tile_key + t);
+                if (k <= p.cap) best = min(best, ((unsigned long long)k << 32) | (unsigned)t);
+            }
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            int verdict = 0;                       // 0 take the tile, 1 nothing pending anywhere: leave, 2 wait and look again, 3 bail out
+            if (best == ~0ull) {
+                int pending = 1;
+                if (lane == 0) {
+                    const uint32_t pub = gated ? __ldcg(p.gfloor + 1) : 0u;
+                    pending = pub ? (int)pub - 1 : atomicAdd(p.gcount, 0);
+                }
+                pending = __shfl_sync(0xffffffffu, pending, 0);
+                verdict = pending <= 0 ? 1 : 2;
+            } else if (gated) {
+                uint32_t fl = 0;
+                if (lane == 0) fl = __ldcg(p.gfloor);
+                fl = __shfl_sync(0xffffffffu, fl, 0);
+                const uint32_t k = (uint32_t)(best >> 32);
+                if (fl != kNoKey && k > fl && k - fl > p.gate) verdict = 2;      // ahead of the wavefront: wait
+            }
+            if (gated && lane == 0) __stcg(p.blk_key + blockIdx.x, best == ~0ull ? kNoKey : (uint32_t)(best >> 32));
+            if (verdict == 2) {
+                if (++idle_spins > (1 << 22)) verdict = 3;
+                else __nanosleep(p.sched_ns);
+            } else idle_spins = 0;
+            if (lane == 0) { sm.best = best; sm.key = (uint32_t)verdict; }
         }
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (lane == 0 && best != ~0ull) atomicMin(&sm.best, best);
         __syncthreads();
         const unsigned long long pick = sm.best;
-        if (gated && tid == 0) __stcg(p.blk_key + blockIdx.x, pick == ~0ull ? kNoKey : (uint32_t)(pick >> 32));
-        if (pick == ~0ull) {
-            int pending = 1;
-            if (tid == 0) {
-                const uint32_t pub = gated ? __ldcg(p.gfloor + 1) : 0u;
-                pending = pub ? (int)pub - 1 : atomicAdd(p.gcount, 0);
-                sm.key = (uint32_t)pending;
-            }
-            __syncthreads();
-            pending = (int)sm.key;
-            __syncthreads();
-            if (pending <= 0) break;
-            if (++idle_spins > (1 << 22)) { if (tid == 0) atomicOr(p.counts + 4, 2); break; }
-            __nanosleep(p.sched_ns);
-            continue;
-        }
-        if (gated) {
-            if (tid == 0) sm.key = __ldcg(p.gfloor);
-            __syncthreads();
-            const uint32_t fl = sm.key;
-            __syncthreads();
-            if (fl != kNoKey && (uint32_t)(pick >> 32) > fl && (uint32_t)(pick >> 32) - fl > p.gate) {      // ahead of the wavefront: wait
-                if (++idle_spins > (1 << 22)) { if (tid == 0) atomicOr(p.counts + 4, 2); break; }
-                __nanosleep(p.sched_ns);
-                continue;
-            }
-        }
-        idle_spins = 0;
+        const int verdict = (int)sm.key;
+        __syncthreads();
+        if (verdict == 1) break;
+        if (verdict == 3) { if (tid == 0) atomicOr(p.counts + 4, 2); break; }
+        if (verdict == 2) continue;
         const int tile = (int)(pick & 0xffffffffu);
         if (tid == 0) {
             sm.key = atomicExch(p.tile_key + tile, kNoKey);
