@@ -293,7 +293,7 @@ static bool use_team_kernel(const nsfs_planner* h, int kind, int algo, int nq) {
     // 8-lane team (5 instead of 3 heap levels per round trip, fewer instructions in sequence): measured on C4, 8 192 queries
     // take 4.2 s one per warp against 5.5 s four per warp, while at 65 536 the team kernel's four-fold query residency wins
     // (profiles/r02_search.md).  So batches that fit two waves of warp slots stay on the wide kernel.
-    return nq > 2 * h->sm_count * 32;
+    return nq > 2 * h->sm_count * 32;                  // (9 472 on a B200)
 }
 
 static int launch_any_search(nsfs_planner* h, bool team, int kind, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,

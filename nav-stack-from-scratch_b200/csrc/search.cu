@@ -74,19 +74,30 @@ __device__ __forceinline__ Prio make_prio(int mode) {
     return p;
 }
 
+// One open list: positions below kWideTop (the top ten levels, 8 KB per warp) in shared memory, the rest in global memory, both
+// reached through one generic pointer chosen with a select.  A sift-down of a 10^4-entry list then makes its first two 5-level
+// chunks at shared-memory latency and only the last one goes to L2 / HBM, and the root is read without a round trip: this is
+// the kernel that serves single queries and small batches, where the time of a launch IS the dependent chain of its longest query.
+constexpr uint32_t kWideTop = 1024;
+struct WideHeap {
+    unsigned long long* a;        // global part (whole array; positions < kWideTop unused when s != a)
+    unsigned long long* s;        // this warp's shared-memory top (== a for a list that lives in one place)
+    __device__ __forceinline__ unsigned long long* at(uint32_t pos) const { return (pos < kWideTop ? s : a) + pos; }
+};
+
 // std::priority_queue::push = push_back + __push_heap (stl_heap.h:135-148), by the whole warp (n is warp-uniform).
 // Positions fit 32 bits (heap_cap <= 8N + 16 < 2^32 / 2 for N < 2^28; larger capacities are refused by search_alloc).
-__device__ __forceinline__ void heap_push(unsigned long long* a, uint32_t& n, unsigned long long v, const Prio prio, int lane) {
+__device__ __forceinline__ void heap_push(const WideHeap hp, uint32_t& n, unsigned long long v, const Prio prio, int lane) {
     const uint32_t pos = n + 1u;                          // array position of the new leaf
     const unsigned long long pv = prio(v);
     const uint32_t q = pos >> lane;                       // lane L >= 1: position of the L-th ancestor (0 = above the root)
     const bool valid = lane >= 1 && q >= 1u;
     unsigned long long e = 0;
-    if (valid) e = a[q];
+    if (valid) e = *hp.at(q);
     const unsigned rise = __ballot_sync(0xffffffffu, valid && prio(e) > pv);    // ancestor sorts after v: it moves down
     const int m = __ffs(~(rise >> 1)) - 1;                // length of the run of such ancestors starting at the parent
-    if (lane >= 1 && lane <= m) a[pos >> (lane - 1)] = e;
-    if (lane == 0) a[pos >> m] = v;
+    if (lane >= 1 && lane <= m) *hp.at(pos >> (lane - 1)) = e;
+    if (lane == 0) *hp.at(pos >> m) = v;
     n = n + 1u;
     __syncwarp();
 }
@@ -103,11 +114,11 @@ __device__ __forceinline__ LaneNode lane_node(int lane) {
 }
 
 // top() + pop() = __pop_heap -> __adjust_heap -> __push_heap (stl_heap.h:224-262), by the whole warp.
-__device__ __forceinline__ void heap_pop(unsigned long long* a, uint32_t& n, const Prio prio, int lane, const LaneNode ln) {
+__device__ __forceinline__ void heap_pop(const WideHeap hp, uint32_t& n, const Prio prio, int lane, const LaneNode ln) {
     const uint32_t len = n - 1u;                          // elements left after the pop
     n = len;
     if (len == 0u) return;
-    const unsigned long long v = a[len + 1u];             // the displaced last element
+    const unsigned long long v = *hp.at(len + 1u);        // the displaced last element
     const unsigned long long pv = prio(v);
     uint32_t c1 = 1u;                                     // position (= heap index + 1) of the hole
     for (;;) {
@@ -115,7 +126,7 @@ __device__ __forceinline__ void heap_pop(unsigned long long* a, uint32_t& n, con
         const uint32_t lpos = 2u * pos;                   // left child's position; it exists iff its heap index lpos-1 < len
         const bool has = lane < 31 && (c1 >> (30 - ln.r)) == 0u && lpos <= len;   // (the shift test keeps pos from wrapping)
         ulonglong2 ch = make_ulonglong2(0ull, 0ull);
-        if (has) ch = *reinterpret_cast<const ulonglong2*>(a + lpos);
+        if (has) ch = *reinterpret_cast<const ulonglong2*>(hp.at(lpos));     // lpos even: both children on one side of kWideTop
         // __adjust_heap: take the right child unless it sorts after the left one; a lone left child is taken as is
         const bool left = !(lpos + 1u <= len) || prio(ch.y) > prio(ch.x);
         const unsigned long long pick = left ? ch.x : ch.y;
@@ -130,11 +141,11 @@ __device__ __forceinline__ void heap_pop(unsigned long long* a, uint32_t& n, con
             node = 2u * node + 2u - ((m_left >> node) & 1u);
             ++steps;
         }
-        if ((path >> lane) & 1u) a[pos] = pick;           // the picked child moves up into my node
+        if ((path >> lane) & 1u) *hp.at(pos) = pick;      // the picked child moves up into my node
         const int rq = 31 - __clz(node + 1u);
         const uint32_t npos = (c1 << rq) + (node + 1u - (1u << rq));
         if (steps < 5u) {
-            if (lane == 0) a[npos] = v;
+            if (lane == 0) *hp.at(npos) = v;
             break;
         }
         c1 = npos;                                        // five levels down and still sinking
@@ -207,14 +218,17 @@ __device__ __forceinline__ bool warp_los(const uint32_t* __restrict__ free_bits,
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 7) search_kernel(SearchParams p) {
+    __shared__ __align__(16) unsigned long long s_top[SEARCH_WARPS_PER_BLOCK][kWideTop];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SEARCH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (slot >= p.slots) return;
     const int W = p.W, H = p.H, mode = p.mode;
     const long long N = p.N;
     uint4* cells = p.cells + (size_t)slot * (size_t)N;
-    unsigned long long* heap = p.heap + (size_t)slot * (size_t)p.heap_stride;
+    WideHeap heap;
+    heap.a = p.heap + (size_t)slot * (size_t)p.heap_stride;
+    heap.s = s_top[threadIdx.x >> 5];
     const Prio prio = make_prio(mode);
     const LaneNode ln = lane_node(lane);
     const uint32_t uW = (uint32_t)W, uN = (uint32_t)N;       // N < 2^29 (nsfs_create)
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 8) search_kernel(
 
         while (status == NSFS_OK && n > 0) {
             // ---- pop (astar.cpp:56) --------------------------------------------------------------------
-            const unsigned long long top = heap[1];            // same address in every lane: one broadcast load
+            const unsigned long long top = heap.s[1];          // the root lives in shared memory: one broadcast load, no round trip
             const uint32_t ku = (uint32_t)(top & kKeyMask);
             const int i = (int)(ku / uW), j = (int)(ku - (uint32_t)i * uW);
             // Everything the expansion reads depends only on ku: issue those loads now, use them after the sift-down.
@@ -454,6 +468,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) fallback_small_ke
     __shared__ __align__(16) FbState sm[SEARCH_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31;
     FbState& st = sm[threadIdx.x >> 5];
+    WideHeap fbh;
+    fbh.a = st.heap; fbh.s = st.heap;                           // the whole list in one (shared) array
     const int W = p.W, H = p.H;
     const uint32_t uW = (uint32_t)W;
     const Prio prio = make_prio(NSFS_MODE_G);                   // the fallback planner is prepared with cost mode "g" (global_planner.cpp:127)
@@ -477,12 +493,12 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) fallback_small_ke
             if (lane == 0) { const int s0 = fb_insert(st, ks); st.g[s0] = 0.0; }
             ncells = 1;
             __syncwarp();
-            heap_push(st.heap, n, make_entry(0.0, 0.0, ks, NSFS_MODE_G), prio, lane);
+            heap_push(fbh, n, make_entry(0.0, 0.0, ks, NSFS_MODE_G), prio, lane);
             pushes = 1; peak = 1;
         }
         while (status == NSFS_OK && n > 0) {
             const uint32_t ku = (uint32_t)(st.heap[1] & kKeyMask);
-            heap_pop(st.heap, n, prio, lane, ln);
+            heap_pop(fbh, n, prio, lane, ln);
             pops++;
             const int su = fb_find(st, ku);                    // every key on the open list is in the table
             if (st.vis[su]) continue;                           // stale entry (djikstra.cpp:197-200)
@@ -531,7 +547,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32) fallback_small_ke
                 if (n >= (uint32_t)(FB_CAP - 2)) { status = NSFS_E_HEAP; break; }
                 if (lane == 0) st.g[sv] = pg;                  // the label changes even when the cell is closed (djikstra.cpp:255-259)
                 __syncwarp();
-                heap_push(st.heap, n, make_entry(pg, 0.0, pk, NSFS_MODE_G), prio, lane);
+                heap_push(fbh, n, make_entry(pg, 0.0, pk, NSFS_MODE_G), prio, lane);
                 pushes++;
                 if (n > peak) peak = n;
             }
@@ -560,7 +576,7 @@ int search_alloc(nsfs_planner* h, int want_slots) {
     long long heap_cap = h->opt_heap_cap > 0 ? h->opt_heap_cap : h->N + 8;
     if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;            // heap positions are 32-bit
     if (want_slots < 1) want_slots = 1;
-    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots : (long long)h->sm_count * 32;
+    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots : (long long)h->sm_count * 24;     // six resident blocks of four warps per SM
     long long slots = want_slots;
     if (slots > cap) slots = cap;
     // reuse: enough slots, or an allocation that was made for at least this many and clamped by free HBM (asking again would
@@ -660,12 +676,16 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
     const int block = SEARCH_WARPS_PER_BLOCK * 32;
     const int grid = (p.slots + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK;
+    if (kind != 1 && algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
-    if (kind == 1) { p.mode = NSFS_MODE_G; search_kernel<kAlgoFallback><<<grid, block, 0, h->stream>>>(p); }
-    else if (algo == NSFS_ASTAR) search_kernel<NSFS_ASTAR><<<grid, block, 0, h->stream>>>(p);
-    else if (algo == NSFS_DJIKSTRA) search_kernel<NSFS_DJIKSTRA><<<grid, block, 0, h->stream>>>(p);
-    else if (algo == NSFS_THETASTAR) search_kernel<NSFS_THETASTAR><<<grid, block, 0, h->stream>>>(p);
-    else return NSFS_E_ARG;
+    // 32 KB of shared memory per block (the open lists' top levels): ask for the carveout that keeps six blocks resident
+#define NSFS_WIDE_LAUNCH(A) do { cudaFuncSetAttribute(search_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+                                 search_kernel<A><<<grid, block, 0, h->stream>>>(p); } while (0)
+    if (kind == 1) { p.mode = NSFS_MODE_G; NSFS_WIDE_LAUNCH(kAlgoFallback); }
+    else if (algo == NSFS_ASTAR) NSFS_WIDE_LAUNCH(NSFS_ASTAR);
+    else if (algo == NSFS_DJIKSTRA) NSFS_WIDE_LAUNCH(NSFS_DJIKSTRA);
+    else NSFS_WIDE_LAUNCH(NSFS_THETASTAR);
+#undef NSFS_WIDE_LAUNCH
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
