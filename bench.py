@@ -737,7 +737,7 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
                 "h2d_bytes_per_step": int(2 * H * W * 4 + total * 16), "d2h_bytes_per_step": int(total * 24 * world),
                 "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps,
                 "path": f"{what}: " + ("GpuAstar::planBatch" if world == 1 else "GpuAstar::planBatchSharded over nsfs_host::DeviceGroup (map broadcast + "
-                        "result all-gather over NCCL, called from C++)") + " on a MapData with pageable std::vector<int> planes (uploaded every call), "
+                        "result all-gather over NCCL, called from C++)") + " on a MapData whose std::vector<int> planes are uploaded on every call (page-locked once by the child: MapSync::EveryCallPinned, its default), "
                         "queries from host memory, per-query results back to the host",
                 "same_results_as_resident_path": e2e_same},
         "gpu_launches": launches_all,

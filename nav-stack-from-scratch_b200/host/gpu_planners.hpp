@@ -23,7 +23,8 @@
 namespace nsfs_host {
 
 // When does the planner re-upload MapData?  The reference reads the caller's vectors afresh on every call
-// (global_planner.cpp:65-73 replaces them whenever a ROS message arrives), so EveryCall is the default.
+// (global_planner.cpp:65-73 replaces them whenever a ROS message arrives), so every call uploads them by default
+// (EveryCallPinned; EveryCall is the same without touching the caller's memory: a pageable copy, ~1.7x slower at 2048^2).
 // EveryCallPinned: same contract as EveryCall, but the caller's two vectors are page-locked once (cudaHostRegister through
 // nsfs_pin_host) and stay registered while their data pointers and sizes do not change (the ROS callbacks copy-assign into
 // the same vectors, global_planner.cpp:65-73, so they do not), which makes the per-call upload a DMA at PCIe speed.
@@ -83,7 +84,7 @@ protected:
 
     nsfs_t* handle_ = nullptr;
     int device_ = 0;
-    MapSync sync_ = MapSync::EveryCall;
+    MapSync sync_ = MapSync::EveryCallPinned;     // the reference's contract (re-read the caller's vectors on every call) at PCIe speed
     bool dirty_ = true;
     bool textbook_graph_ = false;
     nsfs_stats stats_{};
