@@ -115,7 +115,8 @@ struct TeamWork {
     int       slots = 0;
     int       target = 0;          // see SearchWork
     long long heap_cap = 0;
-    uint2*    cells = nullptr;     // [slots][N]   {n_card | n_diag << 16, epoch << 4 | visited << 3 | parent direction}
+    void*     cells = nullptr;     // [slots][N]   8-byte {n_card | n_diag << 16, epoch << 4 | visited << 3 | parent direction} or 4-byte records
+    int       cell_bytes = 8;
     unsigned long long* heap = nullptr;
     uint32_t* epoch = nullptr;
     int*      work_counter = nullptr;
@@ -158,6 +159,7 @@ struct nsfs_planner {
     long long last_ks = 0, last_kg = 0;
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
+    long long opt_team_cell_bytes = 0;  // batch kernel: 0 = by map size (4 up to 2048 cells a side), 4 | 8
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
     long long opt_search_order = 0;     // batches larger than the slots: 0 / 1 = start the longest expected queries first, 2 = input order
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query

@@ -19,9 +19,13 @@
 //         with one 128-bit load; two ballots give the path through the three levels; stop at the first picked child that
 //         sorts after the displaced element (same final array as sink-to-leaf + sift-up, priorities are monotone on a path)
 //   push  lanes 1..7 load ancestors 1..7 of the new leaf, one ballot finds how far the element rises
-// Per-cell record, 8 bytes instead of 16 so that four times as many searches fit in HBM:
-//   x = n_card | n_diag << 16     g = n_card + n_diag * sqrt(2): the label as EXACT step counts (SURVEY.md §7 "hard parts" 6)
-//   y = epoch << 4 | visited << 3 | direction of the edge from the parent (parent key = key - OFF[d])
+// Per-cell record: the label as EXACT step counts, g = n_card + n_diag * sqrt(2) (SURVEY.md §7 "hard parts" 6), in one of two sizes
+//   8 bytes   x = n_card | n_diag << 16, y = epoch << 4 | visited << 3 | direction of the edge from the parent (parent key = key - OFF[d])
+//   4 bytes   n_card : 12 | n_diag : 12 | direction : 3 | visited : 1 | epoch : 4     for maps up to 2048 cells a side (a label
+//             beyond 4095 steps of one kind ends the query with NSFS_E_HEAP like any other overflow).  The 4-bit epoch wraps every 15
+//             queries of a slot, which then clears its records (4 MB at 1024^2, ~0.1 ms against seconds per query).  Half the
+//             footprint per query in flight = more queries in flight and fewer DRAM sectors per expansion: the batch kernel's
+//             throughput is set by both (profiles/r02_search.md §3).
 // Every decision the reference takes on g is reproduced from the integer pair: (int)g and (int)(g + h) cannot differ because
 // a + b*sqrt(2) with b != 0 stays >= 1/(2.83 b) away from any integer (b < 65536 here) while fp64 accumulates < 1e-9 of
 // error, and "g[v] > cand + 1e-5" compares two such numbers whose difference is either exactly 0 or >= 1e-5-clear for
@@ -39,13 +43,14 @@ enum { PH_FETCH = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINAL = 3, PH_DONE = 4 };
 
 struct TeamParams {
     const uint16_t* out_mask;
-    uint2* cells;                 // [slots][N]
+    void* cells;                  // [slots][N] records of 8 or 4 bytes (template parameter CB)
     unsigned long long* heap;     // [slots][heap_stride]
     uint32_t* epoch;              // [slots]
     int* work_counter;
     int H, W;
     long long N;
     long long heap_cap, heap_stride;
+    long long cell_stride;        // bytes per slot of the record array (a multiple of 16)
     int slots;
     int mode;
     int nq;
@@ -61,6 +66,30 @@ struct TeamParams {
     uint32_t div_m;               // key / W = __umulhi(key, div_m) >> div_s, exact for key < 2^29 (set by the launcher)
     int div_s;
 };
+
+// A cell record as loaded (either size); fields are extracted where they are used, so a record costs one or two registers.
+template <int CB>
+struct CellRec {
+    uint32_t x, y;                                       // CB == 4: x is the whole record, y unused
+    __device__ __forceinline__ uint32_t nc() const { return CB == 8 ? (x & 0xffffu) : (x & 0xfffu); }
+    __device__ __forceinline__ uint32_t nd() const { return CB == 8 ? (x >> 16) : ((x >> 12) & 0xfffu); }
+    __device__ __forceinline__ uint32_t dir() const { return CB == 8 ? (y & 7u) : ((x >> 24) & 7u); }
+    __device__ __forceinline__ uint32_t visited() const { return CB == 8 ? ((y >> 3) & 1u) : ((x >> 27) & 1u); }
+    __device__ __forceinline__ bool valid(uint32_t epoch) const { return CB == 8 ? (y >> 4) == epoch : (x >> 28) == epoch; }
+};
+template <int CB>
+__device__ __forceinline__ CellRec<CB> cell_load(const void* base, uint32_t k) {
+    CellRec<CB> c;
+    if (CB == 8) { const uint2 r = __ldcg(reinterpret_cast<const uint2*>(base) + k); c.x = r.x; c.y = r.y; }
+    else { c.x = __ldcg(reinterpret_cast<const uint32_t*>(base) + k); c.y = 0u; }
+    return c;
+}
+template <int CB>
+__device__ __forceinline__ void cell_store(void* base, uint32_t k, uint32_t nc, uint32_t nd, uint32_t dir, uint32_t visited, uint32_t epoch) {
+    if (CB == 8) __stcg(reinterpret_cast<uint2*>(base) + k, make_uint2(nc | (nd << 16), (epoch << 4) | (visited << 3) | dir));
+    else __stcg(reinterpret_cast<uint32_t*>(base) + k, nc | (nd << 12) | (dir << 24) | (visited << 27) | (epoch << 28));
+}
+template <int CB> __device__ __forceinline__ constexpr uint32_t cell_max_steps() { return CB == 8 ? 0xffffu : 0xfffu; }
 
 // the selected comparator's sort key, from an entry's high word
 template <int MODE>
@@ -152,8 +181,8 @@ __device__ __forceinline__ void team_push(const TeamHeap hp, uint32_t& n, unsign
     if (pushing) n = n + 1u;
 }
 
-template <int ALGO, int MODE>
-__global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(TeamParams p) {
+template <int ALGO, int MODE, int CB>
+__global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) search_team_kernel(TeamParams p) {
     __shared__ __align__(16) unsigned long long s_top[TEAM_WARPS_PER_BLOCK * 4][kTopN];
     const int lane = threadIdx.x & 31, tl = lane & 7, tbase = lane & 24;
     const int slot = (blockIdx.x * TEAM_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * 4 + (lane >> 3);
@@ -161,7 +190,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
     constexpr int mode = MODE;
     const uint32_t uW = (uint32_t)W, uN = (uint32_t)p.N;
     const bool have_slot = slot < p.slots;
-    uint2* cells = p.cells + (size_t)(have_slot ? slot : 0) * (size_t)p.N;
+    char* cells = reinterpret_cast<char*>(p.cells) + (size_t)(have_slot ? slot : 0) * (size_t)p.cell_stride;
     TeamHeap heap;
     heap.a = p.heap + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
     heap.s = s_top[(threadIdx.x >> 5) * 4 + (lane >> 3)];
@@ -190,6 +219,13 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 else {
                     qi = p.order ? p.order[q] : q;
                     ++epoch;
+                    if (CB == 4 && epoch > 15u) {
+                        // the 4-bit stamp has gone round: this team wipes its records (128 bytes per step) and starts again at 1
+                        uint4* w = reinterpret_cast<uint4*>(cells);
+                        const size_t n16 = (size_t)p.cell_stride / 16;
+                        for (size_t t = tl; t < n16; t += 8) __stcg(w + t, make_uint4(0u, 0u, 0u, 0u));
+                        epoch = 1u;
+                    }
                     const int si = p.q[4 * qi], sj = p.q[4 * qi + 1];
                     gi = p.q[4 * qi + 2]; gj = p.q[4 * qi + 3];
                     n = 0; peak = 0; pops = 0; expansions = 0; pushes = 0; found = false; status = NSFS_OK; plen = 1;
@@ -207,7 +243,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                         if (f0 > 0xffffu) { status = NSFS_E_HEAP; phase = PH_FINAL; }       // beyond the 16-bit sort key: the wide kernel replays it
                         else {
                             if (tl == 0) {
-                                __stcg(cells + ks, make_uint2(0u, epoch << 4));
+                                cell_store<CB>(cells, ks, 0u, 0u, 0u, 0u, epoch);
                                 heap.st(1u, ((unsigned long long)(f0 << 16) << 32) | (unsigned long long)ks);
                             }
                             n = 1; pushes = 1; peak = 1;
@@ -230,24 +266,23 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
             const uint32_t kv = ku + (uint32_t)my_off;               // my neighbour: flat key; its row follows the column wrap
             int vi = i + my_di;
             { const int vj = j + my_dj; if (vj >= W) vi++; else if (vj < 0) vi--; }
-            uint2 pre = make_uint2(0u, 0u), cu_l = make_uint2(0u, 0u);
+            // the records an expansion needs: every lane its neighbour's AND (same cache line for most) the popped cell's
+            CellRec<CB> pre = {0u, 0u}, cu = {0u, 0u};
             uint32_t om_l = 0;
             if (act) {
-                if (kv < uN) pre = __ldcg(cells + kv);
-                if (tl == 0) cu_l = __ldcg(cells + ku);
+                if (kv < uN) pre = cell_load<CB>(cells, kv);
+                cu = cell_load<CB>(cells, ku);
                 if (tl == 1) om_l = __ldg(p.out_mask + ku);
             }
             team_pop<MODE>(heap, n, act, tl, tbase, nr, no);
-            uint2 cu;
-            cu.x = __shfl_sync(FULL, cu_l.x, 0, 8); cu.y = __shfl_sync(FULL, cu_l.y, 0, 8);
             const uint32_t om = __shfl_sync(FULL, om_l, 1, 8);
             bool expand = act;
             if (act) {
                 pops++;
-                if (cu.y & 8u) expand = false;                       // stale entry (astar.cpp:59-62)
+                if (cu.visited()) expand = false;                    // stale entry (astar.cpp:59-62)
             }
             if (expand) {
-                if (tl == 0) __stcg(&cells[ku].y, cu.y | 8u);
+                if (tl == 0) cell_store<CB>(cells, ku, cu.nc(), cu.nd(), cu.dir(), 1u, epoch);
                 expansions++;
                 if (ku == kg) { found = true; expand = false; phase = PH_WALK; wk = kg; plen = 0; }        // astar.cpp:68
                 else if (om & kThrowBit) { status = NSFS_E_RANGE; expand = false; phase = PH_FINAL; }         // vector::at throws (R6)
@@ -256,15 +291,15 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
             bool relax = false, overflow = false;
             unsigned long long entry = 0;
             if (expand && ((om >> tl) & 1u)) {
-                const bool valid = (pre.y >> 4) == epoch;
+                const bool valid = pre.valid(epoch);
                 const bool diag = ((om >> (8 + tl)) & 1u) && tl;
-                const uint32_t nc = (cu.x & 0xffffu) + (diag ? 0u : 1u), nd = (cu.x >> 16) + (diag ? 1u : 0u);
+                const uint32_t nc = cu.nc() + (diag ? 0u : 1u), nd = cu.nd() + (diag ? 1u : 0u);
                 // astar.cpp:116  g[v] > cand + 1e-5  on labels a + b*sqrt(2) held as exact step counts: with da = a_v - a, db = b_v - b the
                 // difference da + db*sqrt(2) is 0 or at least 1 / (|da| + |db| sqrt(2)) > 1e-5 away from 0 (|da| < 2^16, |db| < 2^14), so the
                 // test is the SIGN of da + db*sqrt(2): decided by the signs, or by da^2 against 2 db^2 when they differ.  Integers only.
                 if (!valid) relax = true;
                 else {
-                    const int da = (int)(pre.x & 0xffffu) - (int)nc, db = (int)(pre.x >> 16) - (int)nd;
+                    const int da = (int)pre.nc() - (int)nc, db = (int)pre.nd() - (int)nd;
                     if (db > -16384 && db < 16384) {
                         if (db == 0) relax = da > 0;
                         else if (da == 0) relax = db > 0;
@@ -275,14 +310,14 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                         }
                     } else {
                         const double cand = __dadd_rn((double)nc, __dmul_rn((double)nd, kSqrt2D));
-                        const double gv = __dadd_rn((double)(pre.x & 0xffffu), __dmul_rn((double)(pre.x >> 16), kSqrt2D));
+                        const double gv = __dadd_rn((double)pre.nc(), __dmul_rn((double)pre.nd(), kSqrt2D));
                         relax = gv > __dadd_rn(cand, kSlack);
                     }
                 }
                 if (relax) {
-                    if (nc > 0xffffu || nd > 0xffffu) { overflow = true; relax = false; }
+                    if (nc > cell_max_steps<CB>() || nd > cell_max_steps<CB>()) { overflow = true; relax = false; }
                     else {
-                        __stcg(cells + kv, make_uint2(nc | (nd << 16), (epoch << 4) | (valid ? (pre.y & 8u) : 0u) | (uint32_t)tl));
+                        cell_store<CB>(cells, kv, nc, nd, (uint32_t)tl, valid ? pre.visited() : 0u, epoch);
                         // keys (grid_planner_core.cpp:385-391): (int)g = a + floor(b sqrt 2); (int)(g + h) with h = ord*sqrt(2) + card (dist_oct
                         // with the row slip, bot_utils.cpp:44-65) = a + card + floor((b + ord) sqrt 2).  k*sqrt(2) stays >= 1 / (2.83 k) away
                         // from every integer and one fp64 product is good to 1e-16 relative, so the truncations are the reference's.
@@ -322,7 +357,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                 int32_t* out = p.paths ? p.paths + (size_t)qi * p.path_cap * 2 : nullptr;
                 if (out && plen < p.path_cap) { out[2 * plen] = (int)(wk / uW); out[2 * plen + 1] = (int)(wk % uW); }
                 if (wk != ks) {
-                    const uint32_t d = __ldcg(cells + wk).y & 7u;
+                    const uint32_t d = cell_load<CB>(cells, wk).dir();
                     nk = wk - (uint32_t)(nb_di((int)d) * W + nb_dj((int)d));
                 }
             }
@@ -348,8 +383,8 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32) search_team_kernel(
                     if (p.g_goal) {
                         double gg = kInfD;
                         if (kg != 0xffffffffu) {
-                            const uint2 c = __ldcg(cells + kg);
-                            if ((c.y >> 4) == epoch) gg = __dadd_rn((double)(c.x & 0xffffu), __dmul_rn((double)(c.x >> 16), kSqrt2D));
+                            const CellRec<CB> c = cell_load<CB>(cells, kg);
+                            if (c.valid(epoch)) gg = __dadd_rn((double)c.nc(), __dmul_rn((double)c.nd(), kSqrt2D));
                         }
                         p.g_goal[qi] = gg;
                     }
@@ -426,34 +461,47 @@ __global__ void __launch_bounds__(1024) team_order_kernel(const int32_t* __restr
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
+// 4-byte records for maps up to 2048 cells a side (12-bit step counts), 8-byte records beyond; "team_cell_bytes" overrides.
+static int team_cell_bytes(const nsfs_planner* h) {
+    if (h->opt_team_cell_bytes == 4 || h->opt_team_cell_bytes == 8) return (int)h->opt_team_cell_bytes;
+    return (h->H <= 2048 && h->W <= 2048) ? 4 : 8;
+}
+
 int team_alloc(nsfs_planner* h, int want_slots) {
     TeamWork& s = h->team;
-    long long heap_cap = h->opt_team_heap_cap > 0 ? h->opt_team_heap_cap : (h->N / 8 > 4096 ? h->N / 8 : 4096);
+    const int cb = team_cell_bytes(h);
+    // open-list slot: N / 8 entries with 8-byte records (round 1), N / 32 with 4-byte records, where the point is the footprint
+    // (a C4 query peaks at ~11 000 entries of the 32 768 it then gets); an overflow re-runs the query on the wide kernel either way
+    const long long auto_cap = cb == 4 ? h->N / 32 : h->N / 8;
+    long long heap_cap = h->opt_team_heap_cap > 0 ? h->opt_team_heap_cap : (auto_cap > 4096 ? auto_cap : 4096);
     if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;
     if (want_slots < 1) want_slots = 1;
-    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * 28 * 4;    // 28 warps / SM x 4 teams: what 0.85 of a B200's HBM
-                                                                                                           // holds at 1024^2 (9 MB per slot); 24 -> 28 warps measured +6 % queries/s
+    // warps of slots per SM: 28 with 8-byte records (what 0.85 of a B200's HBM holds at 1024^2, 9 MB per slot), 36 with 4-byte
+    // records (the register file's limit at 55 registers per thread; 4.25 MB per slot)
+    const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * (cb == 4 ? 36 : 28) * 4;
     long long slots = want_slots < cap ? want_slots : cap;
     // reuse: enough slots, or an allocation made for at least this many that free HBM clamped (see search_alloc)
-    if (s.cells && s.heap_cap >= heap_cap && (s.slots >= slots || s.target >= slots)) return NSFS_OK;
+    if (s.cells && s.cell_bytes == cb && s.heap_cap >= heap_cap && (s.slots >= slots || s.target >= slots)) return NSFS_OK;
     team_free(h);
     const long long target = slots;
     size_t free_b = 0, total_b = 0;
     NSFS_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
     const long long heap_stride = (heap_cap + 5) & ~1ll;
-    const size_t per_slot = (size_t)h->N * sizeof(uint2) + (size_t)heap_stride * sizeof(unsigned long long);
+    const size_t cell_stride = (((size_t)h->N * cb + 15) / 16) * 16;      // per-slot record arrays stay 16-byte aligned (the epoch wipe stores uint4)
+    const size_t per_slot = cell_stride + (size_t)heap_stride * sizeof(unsigned long long);
     const long long fit = (long long)((double)free_b * 0.85 / (double)per_slot);
     if (slots > fit) slots = fit;
     if (slots < 1) return NSFS_E_NOMEM;
-    NSFS_CUDA_TRY(h, cudaMalloc(&s.cells, (size_t)slots * (size_t)h->N * sizeof(uint2)));
+    NSFS_CUDA_TRY(h, cudaMalloc(&s.cells, (size_t)slots * cell_stride));
     NSFS_CUDA_TRY(h, cudaMalloc(&s.heap, (size_t)slots * (size_t)heap_stride * sizeof(unsigned long long)));
     NSFS_CUDA_TRY(h, cudaMalloc(&s.epoch, (size_t)slots * sizeof(uint32_t)));
     NSFS_CUDA_TRY(h, cudaMalloc(&s.work_counter, sizeof(int)));
-    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * (size_t)h->N * sizeof(uint2), h->stream));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.cells, 0, (size_t)slots * cell_stride, h->stream));
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.epoch, 0, (size_t)slots * sizeof(uint32_t), h->stream));
     s.slots = (int)slots;
     s.target = (int)target;
     s.heap_cap = heap_cap;
+    s.cell_bytes = cb;
     return NSFS_OK;
 }
 
@@ -472,6 +520,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     TeamParams p;
     p.out_mask = h->d_out_mask; p.cells = s.cells; p.heap = s.heap; p.epoch = s.epoch; p.work_counter = s.work_counter;
     p.H = h->H; p.W = h->W; p.N = h->N; p.heap_cap = s.heap_cap; p.heap_stride = (s.heap_cap + 5) & ~1ll;
+    p.cell_stride = (long long)((((size_t)h->N * s.cell_bytes + 15) / 16) * 16);
     p.slots = nq < s.slots ? nq : s.slots;
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
@@ -503,8 +552,9 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA) return NSFS_E_ARG;
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
     // 16 KB of shared memory per block (the open lists' top levels) x 7 resident blocks: ask for a carveout that holds them
-#define NSFS_TEAM_LAUNCH(A, M) do { cudaFuncSetAttribute(search_team_kernel<A, M>, cudaFuncAttributePreferredSharedMemoryCarveout, 60); \
-                                    search_team_kernel<A, M><<<grid, block, 0, h->stream>>>(p); } while (0)
+#define NSFS_TEAM_LAUNCH1(A, M, C) do { cudaFuncSetAttribute(search_team_kernel<A, M, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 70); \
+                                       search_team_kernel<A, M, C><<<grid, block, 0, h->stream>>>(p); } while (0)
+#define NSFS_TEAM_LAUNCH(A, M) do { if (s.cell_bytes == 4) NSFS_TEAM_LAUNCH1(A, M, 4); else NSFS_TEAM_LAUNCH1(A, M, 8); } while (0)
     if (algo == NSFS_ASTAR) {
         if (p.mode == NSFS_MODE_F) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_F);
         else if (p.mode == NSFS_MODE_G) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_G);
@@ -515,6 +565,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
         else NSFS_TEAM_LAUNCH(NSFS_DJIKSTRA, NSFS_MODE_FG);
     }
 #undef NSFS_TEAM_LAUNCH
+#undef NSFS_TEAM_LAUNCH1
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
