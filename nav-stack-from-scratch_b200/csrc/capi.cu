@@ -841,6 +841,7 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "max_slots")) { h->opt_max_slots = value; search_free(h); team_free(h); return NSFS_OK; }
     if (!strcmp(key, "heap_cap")) { h->opt_heap_cap = value; search_free(h); return NSFS_OK; }
     if (!strcmp(key, "team_heap_cap")) { h->opt_team_heap_cap = value; team_free(h); return NSFS_OK; }
+    if (!strcmp(key, "team_entry_bytes")) { h->opt_team_entry_bytes = value; return NSFS_OK; }
     if (!strcmp(key, "team_cell_bytes")) { h->opt_team_cell_bytes = value; team_free(h); return NSFS_OK; }
     if (!strcmp(key, "search_kernel")) { h->opt_search_kernel = value; return NSFS_OK; }
     if (!strcmp(key, "search_order")) { h->opt_search_order = value; return NSFS_OK; }

@@ -159,6 +159,7 @@ struct nsfs_planner {
     long long last_ks = 0, last_kg = 0;
     long long opt_max_slots = 0;        // 0 = auto
     long long opt_heap_cap = 0;         // 0 = auto (N entries)
+    long long opt_team_entry_bytes = 0; // batch kernel: 0 = 4-byte open-list entries where cost mode "f" and N <= 2^20 allow, 8 = always 8-byte
     long long opt_team_cell_bytes = 0;  // batch kernel: 0 = by map size (4 up to 2048 cells a side), 4 | 8
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
     long long opt_search_order = 0;     // batches larger than the slots: 0 / 1 = start the longest expected queries first, 2 = input order

@@ -38,13 +38,12 @@ namespace nsfs {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TEAM_WARPS_PER_BLOCK = 4;
-constexpr uint32_t kTopN = 128;          // heap positions < kTopN are held in shared memory (levels 0..6)
 enum { PH_FETCH = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINAL = 3, PH_DONE = 4 };
 
 struct TeamParams {
     const uint16_t* out_mask;
     void* cells;                  // [slots][N] records of 8 or 4 bytes (template parameter CB)
-    unsigned long long* heap;     // [slots][heap_stride]
+    void* heap;                   // [slots][heap_stride] entries of 8 or 4 bytes (template parameter EB)
     uint32_t* epoch;              // [slots]
     int* work_counter;
     int H, W;
@@ -91,7 +90,16 @@ __device__ __forceinline__ void cell_store(void* base, uint32_t k, uint32_t nc, 
 }
 template <int CB> __device__ __forceinline__ constexpr uint32_t cell_max_steps() { return CB == 8 ? 0xffffu : 0xfffu; }
 
-// the selected comparator's sort key, from an entry's high word
+// Open-list entries come in two sizes (template parameter EB):
+//   8 bytes   high word (int)f : 16 | (int)g : 16, low word flat key            any cost mode, any map
+//   4 bytes   (int)f : 12 | flat key : 20                                         cost mode "f" on maps of up to 2^20 cells: that
+//             comparator never looks at g (grid_planner_core.cpp:55-59), so the entry need not carry it; half the bytes per heap
+//             level, and the shared-memory top holds eight levels instead of seven.  f beyond 12 bits -> NSFS_E_HEAP (wide kernel).
+template <int EB> struct EntryT { typedef unsigned long long type; typedef ulonglong2 pair; };
+template <> struct EntryT<4> { typedef uint32_t type; typedef uint2 pair; };
+template <int EB> __device__ __forceinline__ constexpr uint32_t top_n() { return EB == 4 ? 256u : 128u; }     // entries of the shared-memory top (1 KB)
+
+// the selected comparator's sort key
 template <int MODE>
 __device__ __forceinline__ uint32_t prio_of(unsigned long long e) {
     const uint32_t hi = (uint32_t)(e >> 32);
@@ -99,29 +107,36 @@ __device__ __forceinline__ uint32_t prio_of(unsigned long long e) {
     if (MODE == NSFS_MODE_G) return hi & 0xffffu;        // g only            (61-65)
     return hi;                                           // f, then smaller g (67-75)
 }
+template <int MODE>
+__device__ __forceinline__ uint32_t prio_of(uint32_t e) { return e >> 20; }      // 4-byte entries exist for MODE_F only
+template <int EB> __device__ __forceinline__ uint32_t entry_key(typename EntryT<EB>::type e) { return EB == 4 ? ((uint32_t)e & 0xfffffu) : (uint32_t)e; }
 
 __device__ __forceinline__ unsigned team_ballot(bool pred, int tbase) { return (__ballot_sync(FULL, pred) >> tbase) & 0xffu; }
 
-// One open list: positions < kTopN in shared memory, the rest in global memory; position = heap index + 1.  Both halves are
+// One open list: positions < top_n (1 KB worth of entries) in shared memory, the rest in global memory; position = heap index + 1.  Both halves are
 // reached through ONE generic pointer chosen with a select (no branch): the first version of this split branched per access and
 // its extra ~80 instructions per pop cost more than the saved round trips (ncu, round 2: the accessors were 20 % of all
 // instructions and the kernel is bound by how many it issues in sequence, not by memory).
+template <int EB>
 struct TeamHeap {
-    unsigned long long* a;        // global part (whole array; positions < kTopN unused)
-    unsigned long long* s;        // generic pointer to this team's shared-memory top
-    __device__ __forceinline__ unsigned long long* at(uint32_t pos) const { return (pos < kTopN ? s : a) + pos; }
-    __device__ __forceinline__ unsigned long long ld(uint32_t pos) const { return *at(pos); }
-    __device__ __forceinline__ void st(uint32_t pos, unsigned long long v) const { *at(pos) = v; }
-    __device__ __forceinline__ ulonglong2 ld_pair(uint32_t lpos) const {     // lpos even: both children on the same side of kTopN
-        return *reinterpret_cast<const ulonglong2*>(at(lpos));
+    typedef typename EntryT<EB>::type E;
+    typedef typename EntryT<EB>::pair P;
+    E* a;        // global part (whole array; positions < top_n unused)
+    E* s;        // generic pointer to this team's shared-memory top
+    __device__ __forceinline__ E* at(uint32_t pos) const { return (pos < top_n<EB>() ? s : a) + pos; }
+    __device__ __forceinline__ E ld(uint32_t pos) const { return *at(pos); }
+    __device__ __forceinline__ void st(uint32_t pos, E v) const { *at(pos) = v; }
+    __device__ __forceinline__ P ld_pair(uint32_t lpos) const {     // lpos even: both children on the same side of top_n
+        return *reinterpret_cast<const P*>(at(lpos));
     }
 };
 
 // std::pop_heap for every team with act set (each on its own array); warp-uniform control flow.
-template <int MODE>
-__device__ __forceinline__ void team_pop(const TeamHeap hp, uint32_t& n, bool act, int tl, int tbase, int r, uint32_t o) {
+template <int MODE, int EB>
+__device__ __forceinline__ void team_pop(const TeamHeap<EB> hp, uint32_t& n, bool act, int tl, int tbase, int r, uint32_t o) {
+    typedef typename EntryT<EB>::type E;
     uint32_t len = 0, pv = 0;
-    unsigned long long v = 0;
+    E v = 0;
     bool sinking = false;
     if (act) {
         len = n - 1u;
@@ -133,10 +148,11 @@ __device__ __forceinline__ void team_pop(const TeamHeap hp, uint32_t& n, bool ac
         const uint32_t pos = (c1 << r) + o;               // my node; its children sit at positions 2*pos, 2*pos + 1
         const uint32_t lpos = 2u * pos;
         const bool has = sinking && tl < 7 && (c1 >> (30 - r)) == 0u && lpos <= len;
-        ulonglong2 ch = make_ulonglong2(0ull, 0ull);
+        typename EntryT<EB>::pair ch;
+        ch.x = 0; ch.y = 0;
         if (has) ch = hp.ld_pair(lpos);
         const bool left = !(lpos + 1u <= len) || prio_of<MODE>(ch.y) > prio_of<MODE>(ch.x);      // right child unless it sorts after the left one
-        const unsigned long long pick = left ? ch.x : ch.y;
+        const E pick = left ? ch.x : ch.y;
         const bool stop = !has || prio_of<MODE>(pick) > pv;
         const unsigned m_left = team_ballot(left, tbase);
         const unsigned m_stop = team_ballot(stop, tbase);
@@ -159,15 +175,16 @@ __device__ __forceinline__ void team_pop(const TeamHeap hp, uint32_t& n, bool ac
 }
 
 // std::push_heap for every team with pushing set.
-template <int MODE>
-__device__ __forceinline__ void team_push(const TeamHeap hp, uint32_t& n, unsigned long long v, bool pushing, int tl, int tbase) {
+template <int MODE, int EB>
+__device__ __forceinline__ void team_push(const TeamHeap<EB> hp, uint32_t& n, typename EntryT<EB>::type v, bool pushing, int tl, int tbase) {
+    typedef typename EntryT<EB>::type E;
     uint32_t base = n + 1u;                               // position of the hole the new element rises from
     const uint32_t pv = prio_of<MODE>(v);
     bool rising = pushing;
     while (__any_sync(FULL, rising)) {
         const uint32_t q = base >> tl;                    // tl >= 1: position of the tl-th ancestor of the hole
         const bool valid = rising && tl >= 1 && q >= 1u;
-        unsigned long long e = 0;
+        E e = 0;
         if (valid) e = hp.ld(q);
         const unsigned rise = team_ballot(valid && prio_of<MODE>(e) > pv, tbase);
         const int m = __ffs(~(rise >> 1)) - 1;            // run of ancestors (from the parent up) that sort after v: 0..7
@@ -181,9 +198,11 @@ __device__ __forceinline__ void team_push(const TeamHeap hp, uint32_t& n, unsign
     if (pushing) n = n + 1u;
 }
 
-template <int ALGO, int MODE, int CB>
+template <int ALGO, int MODE, int CB, int EB>
 __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) search_team_kernel(TeamParams p) {
-    __shared__ __align__(16) unsigned long long s_top[TEAM_WARPS_PER_BLOCK * 4][kTopN];
+    typedef typename EntryT<EB>::type E;
+    static_assert(EB == 8 || MODE == NSFS_MODE_F, "4-byte entries carry f only");
+    __shared__ __align__(16) E s_top[TEAM_WARPS_PER_BLOCK * 4][top_n<EB>()];
     const int lane = threadIdx.x & 31, tl = lane & 7, tbase = lane & 24;
     const int slot = (blockIdx.x * TEAM_WARPS_PER_BLOCK + (threadIdx.x >> 5)) * 4 + (lane >> 3);
     const int W = p.W;
@@ -191,8 +210,8 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
     const uint32_t uW = (uint32_t)W, uN = (uint32_t)p.N;
     const bool have_slot = slot < p.slots;
     char* cells = reinterpret_cast<char*>(p.cells) + (size_t)(have_slot ? slot : 0) * (size_t)p.cell_stride;
-    TeamHeap heap;
-    heap.a = p.heap + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
+    TeamHeap<EB> heap;
+    heap.a = reinterpret_cast<E*>(p.heap) + (size_t)(have_slot ? slot : 0) * (size_t)p.heap_stride;
     heap.s = s_top[(threadIdx.x >> 5) * 4 + (lane >> 3)];
     const int nr = 31 - __clz(tl + 1);                    // my node of a 3-level subtree: level 0,1,1,2,2,2,2 (lane 7: unused)
     const uint32_t no = (uint32_t)(tl + 1) - (1u << nr);
@@ -240,11 +259,11 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
                             h0 = __dadd_rn(__dmul_rn((double)min(ax, ay), kSqrt2D), (double)abs(ax - ay));
                         }
                         const uint32_t f0 = (mode == NSFS_MODE_G) ? 0u : (uint32_t)__double2int_rz(h0);
-                        if (f0 > 0xffffu) { status = NSFS_E_HEAP; phase = PH_FINAL; }       // beyond the 16-bit sort key: the wide kernel replays it
+                        if (f0 > (EB == 4 ? 0xfffu : 0xffffu)) { status = NSFS_E_HEAP; phase = PH_FINAL; }     // beyond the entry's sort key: the wide kernel replays it
                         else {
                             if (tl == 0) {
                                 cell_store<CB>(cells, ks, 0u, 0u, 0u, 0u, epoch);
-                                heap.st(1u, ((unsigned long long)(f0 << 16) << 32) | (unsigned long long)ks);
+                                heap.st(1u, EB == 4 ? (E)((f0 << 20) | ks) : (E)(((unsigned long long)(f0 << 16) << 32) | (unsigned long long)ks));
                             }
                             n = 1; pushes = 1; peak = 1;
                             phase = PH_SEARCH;
@@ -259,9 +278,9 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
         // ---- one pop + expansion for every searching team ------------------------------------------------------------
         {
             const bool act = phase == PH_SEARCH;
-            unsigned long long top = 0;
+            E top = 0;
             if (act) top = heap.s[1];                                // the root is always in shared memory
-            const uint32_t ku = (uint32_t)top;
+            const uint32_t ku = entry_key<EB>(top);
             const int i = (int)(__umulhi(ku, p.div_m) >> p.div_s), j = (int)(ku - (uint32_t)i * uW);
             const uint32_t kv = ku + (uint32_t)my_off;               // my neighbour: flat key; its row follows the column wrap
             int vi = i + my_di;
@@ -274,7 +293,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
                 cu = cell_load<CB>(cells, ku);
                 if (tl == 1) om_l = __ldg(p.out_mask + ku);
             }
-            team_pop<MODE>(heap, n, act, tl, tbase, nr, no);
+            team_pop<MODE, EB>(heap, n, act, tl, tbase, nr, no);
             const uint32_t om = __shfl_sync(FULL, om_l, 1, 8);
             bool expand = act;
             if (act) {
@@ -289,7 +308,7 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
             }
             // ---- my neighbour (astar.cpp:89-124) ----------------------------------------------------------------------
             bool relax = false, overflow = false;
-            unsigned long long entry = 0;
+            E entry = 0;
             if (expand && ((om >> tl) & 1u)) {
                 const bool valid = pre.valid(epoch);
                 const bool diag = ((om >> (8 + tl)) & 1u) && tl;
@@ -329,8 +348,13 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
                                 fi = nc + (uint32_t)abs(ax - ay) + (uint32_t)__double2int_rz(__dmul_rn((double)(nd + (uint32_t)min(ax, ay)), kSqrt2D));
                             } else fi = gi32;
                         }
-                        if (fi > 0xffffu || gi32 > 0xffffu) { overflow = true; relax = false; }     // (the record is written; the query is abandoned anyway)
-                        entry = ((unsigned long long)((fi << 16) | (gi32 & 0xffffu)) << 32) | (unsigned long long)kv;
+                        if (EB == 4) {
+                            if (fi > 0xfffu) { overflow = true; relax = false; }                   // (the record is written; the query is abandoned anyway)
+                            entry = (E)((fi << 20) | kv);
+                        } else {
+                            if (fi > 0xffffu || gi32 > 0xffffu) { overflow = true; relax = false; }
+                            entry = (E)(((unsigned long long)((fi << 16) | (gi32 & 0xffffu)) << 32) | (unsigned long long)kv);
+                        }
                     }
                 }
             }
@@ -341,9 +365,9 @@ __global__ void __launch_bounds__(TEAM_WARPS_PER_BLOCK * 32, CB == 4 ? 9 : 7) se
                 bool pushing = rb != 0u;
                 const int src = pushing ? __ffs(rb) - 1 : 0;
                 rb &= rb - 1u;
-                const unsigned long long v = __shfl_sync(FULL, entry, src, 8);
+                const E v = __shfl_sync(FULL, entry, src, 8);
                 if (pushing && (long long)n >= p.heap_cap) { status = NSFS_E_HEAP; pushing = false; rb = 0; phase = PH_FINAL; }
-                team_push<MODE>(heap, n, v, pushing, tl, tbase);
+                team_push<MODE, EB>(heap, n, v, pushing, tl, tbase);
                 if (pushing) { pushes++; if (n > peak) peak = n; }
             }
             if (phase == PH_SEARCH && n == 0u) phase = PH_FINAL;        // open list exhausted: unreachable (astar.cpp:129-135)
@@ -467,6 +491,12 @@ static int team_cell_bytes(const nsfs_planner* h) {
     return (h->H <= 2048 && h->W <= 2048) ? 4 : 8;
 }
 
+// 4-byte open-list entries where the comparator is "f" and a key fits 20 bits; decided per LAUNCH (the slot is sized for 8-byte ones)
+static int team_entry_bytes(const nsfs_planner* h, int mode) {
+    if (h->opt_team_entry_bytes == 8) return 8;
+    return (mode == NSFS_MODE_F && h->N <= (1ll << 20)) ? 4 : 8;
+}
+
 int team_alloc(nsfs_planner* h, int want_slots) {
     TeamWork& s = h->team;
     const int cb = team_cell_bytes(h);
@@ -552,10 +582,15 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA) return NSFS_E_ARG;
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
     // 16 KB of shared memory per block (the open lists' top levels) x 7 resident blocks: ask for a carveout that holds them
-#define NSFS_TEAM_LAUNCH1(A, M, C) do { cudaFuncSetAttribute(search_team_kernel<A, M, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 70); \
-                                       search_team_kernel<A, M, C><<<grid, block, 0, h->stream>>>(p); } while (0)
-#define NSFS_TEAM_LAUNCH(A, M) do { if (s.cell_bytes == 4) NSFS_TEAM_LAUNCH1(A, M, 4); else NSFS_TEAM_LAUNCH1(A, M, 8); } while (0)
-    if (algo == NSFS_ASTAR) {
+#define NSFS_TEAM_LAUNCH2(A, M, C, B) do { cudaFuncSetAttribute(search_team_kernel<A, M, C, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 70); \
+                                          search_team_kernel<A, M, C, B><<<grid, block, 0, h->stream>>>(p); } while (0)
+#define NSFS_TEAM_LAUNCH1(A, M, B) do { if (s.cell_bytes == 4) NSFS_TEAM_LAUNCH2(A, M, 4, B); else NSFS_TEAM_LAUNCH2(A, M, 8, B); } while (0)
+#define NSFS_TEAM_LAUNCH(A, M) NSFS_TEAM_LAUNCH1(A, M, 8)
+    const bool small_entries = team_entry_bytes(h, p.mode) == 4;
+    if (small_entries) {
+        p.heap_stride *= 2;                    // the same slot bytes, counted in 4-byte entries
+        if (algo == NSFS_ASTAR) NSFS_TEAM_LAUNCH1(NSFS_ASTAR, NSFS_MODE_F, 4); else NSFS_TEAM_LAUNCH1(NSFS_DJIKSTRA, NSFS_MODE_F, 4);
+    } else if (algo == NSFS_ASTAR) {
         if (p.mode == NSFS_MODE_F) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_F);
         else if (p.mode == NSFS_MODE_G) NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_G);
         else NSFS_TEAM_LAUNCH(NSFS_ASTAR, NSFS_MODE_FG);
@@ -566,6 +601,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     }
 #undef NSFS_TEAM_LAUNCH
 #undef NSFS_TEAM_LAUNCH1
+#undef NSFS_TEAM_LAUNCH2
     NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
