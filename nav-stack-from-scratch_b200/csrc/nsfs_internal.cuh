@@ -108,6 +108,8 @@ struct SearchWork {
     unsigned long long* heap = nullptr;  // [slots][heap_cap]
     uint32_t* epoch = nullptr;     // [slots]
     int*      work_counter = nullptr;
+    int32_t*  order = nullptr;     // start order of a batch larger than the slots (see team_order_kernel)
+    int       order_cap = 0;
 };
 
 struct TeamWork {
@@ -212,6 +214,8 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
 
 int team_alloc(nsfs_planner* h, int want_slots);
 void team_free(nsfs_planner* h);
+// order[k] = the k-th query to start, longest expected first (search_team.cu: team_order_kernel); both batch launchers use it
+void launch_start_order(nsfs_planner* h, const int32_t* d_q, int nq, bool heuristic, int32_t* d_order);
 int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status, double* d_g_goal,
                        int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5);
 

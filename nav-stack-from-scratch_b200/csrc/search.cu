@@ -57,6 +57,7 @@ struct SearchParams {
     int32_t* paths;               // optional [nq][path_cap][2]; fallback: [nq][2] result cell
     int path_cap;
     long long* stats5;            // pops, expansions, pushes, heap_peak (max), los_checks
+    const int32_t* order;         // order[k] = the k-th query to start (longest expected first), or nullptr = input order
 };
 
 // Heap storage: heap index x lives at array position x + 1 (position 0 unused), so the two children of x
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, 7) search_kernel(
         if (lane == 0) qi = atomicAdd(p.work_counter, 1);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= p.nq) break;
+        if (p.order) qi = p.order[qi];
         ++epoch;
 
         int si, sj, gi = -1, gj = -1;
@@ -605,7 +607,7 @@ int search_alloc(nsfs_planner* h, int want_slots) {
 
 void search_free(nsfs_planner* h) {
     SearchWork& s = h->search;
-    cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter);
+    cudaFree(s.cells); cudaFree(s.heap); cudaFree(s.epoch); cudaFree(s.work_counter); cudaFree(s.order);
     s = SearchWork();
     if (h->last_plan_kind == 1) h->last_plan_kind = 0;      // the parent store nsfs_last_path would walk is gone
 }
@@ -673,6 +675,16 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;     // unknown => fg (grid_planner_core.cpp:274-281)
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
     p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;
+    p.order = nullptr;
+    if (kind != 1 && nq > p.slots && h->opt_search_order != 2) {     // more queries than slots: start the long ones first
+        if (s.order_cap < nq) {
+            cudaFree(s.order); s.order = nullptr; s.order_cap = 0;
+            NSFS_CUDA_TRY(h, cudaMalloc(&s.order, (size_t)nq * sizeof(int32_t)));
+            s.order_cap = nq;
+        }
+        launch_start_order(h, d_q, nq, algo != NSFS_DJIKSTRA, s.order);
+        p.order = s.order;
+    }
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
     const int block = SEARCH_WARPS_PER_BLOCK * 32;
     const int grid = (p.slots + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK;

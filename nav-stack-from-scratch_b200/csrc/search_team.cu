@@ -484,6 +484,11 @@ __global__ void __launch_bounds__(1024) team_order_kernel(const int32_t* __restr
     for (int k = tid; k < nq; k += 1024) order[atomicAdd(&s_cnt[bucket(k)], 1)] = k;
 }
 
+void launch_start_order(nsfs_planner* h, const int32_t* d_q, int nq, bool heuristic, int32_t* d_order) {
+    team_order_kernel<<<1, 1024, 0, h->stream>>>(d_q, nq, h->H > h->W ? h->H : h->W, heuristic ? 1 : 0, d_order);
+    h->launches++;
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 // 4-byte records for maps up to 2048 cells a side (12-bit step counts), 8-byte records beyond; "team_cell_bytes" overrides.
 static int team_cell_bytes(const nsfs_planner* h) {
@@ -562,8 +567,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
             NSFS_CUDA_TRY(h, cudaMalloc(&s.order, (size_t)nq * sizeof(int32_t)));
             s.order_cap = nq;
         }
-        team_order_kernel<<<1, 1024, 0, h->stream>>>(d_q, nq, h->H > h->W ? h->H : h->W, algo == NSFS_ASTAR ? 1 : 0, s.order);
-        h->launches++;
+        launch_start_order(h, d_q, nq, algo == NSFS_ASTAR, s.order);
         p.order = s.order;
     }
     NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
