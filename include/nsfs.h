@@ -257,9 +257,13 @@ void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the hand
  *                    so the result is the same bits whatever they are set to
  *   "search_kernel"  0 auto | 1 one query per warp | 2 four queries per warp;   "search_order"  2 = start a batch in input order
  *   "max_slots", "heap_cap", "team_heap_cap"   query slots (in warps) and open-list capacity per slot
+ *   "team_cell_bytes"  4 | 8: per-cell record of the batch kernel (0 = 4 up to 2048 cells a side);  "team_entry_bytes"  8 = always
+ *                    8-byte open-list entries (0 = 4-byte ones where cost mode "f" and at most 2^20 cells allow)
+ *   "split_wide"     k > 0: the k longest expected queries of a batch run one per warp on a second stream beside the batch
+ *                    kernel (measured slower - the two kernels do not overlap - so off by default)
  *   "active_row_lo/hi", "count_row_lo/hi"      row windows of a shard (see the row-partitioned field above)
  * Environment overrides read by nsfs_create (experiments / running the test-suite per solver): NSFS_FIELD_MODE, NSFS_FIELD_FENCE,
- * NSFS_SEARCH_ORDER, NSFS_MAX_SLOTS. */
+ * NSFS_SEARCH_ORDER, NSFS_MAX_SLOTS, NSFS_SPLIT_WIDE, NSFS_FIELD_GATE. */
 int         nsfs_set_option(nsfs_t* h, const char* key, long long value);
 const char* nsfs_strerror(int code);
 const char* nsfs_last_cuda_error(const nsfs_t* h);

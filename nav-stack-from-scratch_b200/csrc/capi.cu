@@ -103,6 +103,7 @@ int nsfs_create(nsfs_t** out, int H, int W, int device) {
     if (rc != NSFS_OK) { nsfs_destroy(h); return rc; }
     if (const char* e = getenv("NSFS_FIELD_FENCE")) h->opt_field_fence = atoi(e);
     if (const char* e = getenv("NSFS_SEARCH_ORDER")) h->opt_search_order = atoi(e);
+    if (const char* e = getenv("NSFS_SPLIT_WIDE")) h->opt_split_wide = atoi(e);
     if (const char* e = getenv("NSFS_MAX_SLOTS")) h->opt_max_slots = atoll(e);    // warps of query slots (experiments)
     if (const char* e = getenv("NSFS_FIELD_GATE")) h->opt_field_gate = atoi(e);
     if (const char* e = getenv("NSFS_FIELD_MODE")) h->opt_field_mode = atoi(e);   // default field solver of new handles (tests run the suite per solver)
@@ -126,6 +127,9 @@ void nsfs_destroy(nsfs_t* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -296,13 +300,85 @@ static bool use_team_kernel(const nsfs_planner* h, int kind, int algo, int nq) {
     return nq > 2 * h->sm_count * 32;                  // (9 472 on a B200)
 }
 
+// Split batches (option "split_wide" = k > 0; off by default).  A launch lasts as long as its slowest query, and the slowest C4
+// queries (900 000 expansions) take several seconds on an 8-lane team under full load while a 32-lane warp walks the same chain
+// about twice as fast; so the head of the start order (the k longest expected queries, team_order_kernel) can go to the wide kernel
+// on a second stream while the team kernel takes the rest.  Statuses, paths and settled counts do not depend on which kernel ran a
+// query (costs agree to the last few ulps: fp64 sums there, a + b * sqrt(2) here).  MEASURED: on this driver the two kernels do not
+// overlap - 16 384 C4 queries take 8.2 s split against 6.1 s on the team kernel alone, the same with 592, 1 184 or 2 368 wide
+// queries and with either carveout (profiles/r02_search.md) - so nothing selects it; it stays as a tested option for whoever
+// finds what serialises them.
+static int split_wide_count(const nsfs_planner* h, int nq) {
+    if (h->opt_split_wide <= 0 || h->opt_search_order == 2) return 0;
+    long long k = h->opt_split_wide;
+    if (k > nq / 4) k = nq / 4;
+    if (h->opt_max_slots > 0 && k > h->opt_max_slots) k = h->opt_max_slots;
+    return k < 4 ? 0 : (int)k;
+}
+
+// Per-query state for the kernel(s) a batch of nq will run on.  The two kernels' state competes for the same HBM: a plain batch
+// frees the other kernel's; a split batch keeps k wide slots and gives the team kernel what the rest of HBM holds.
+static int alloc_for_search(nsfs_planner* h, bool team, int nq) {
+    if (!team) {
+        if (nq > 1 && h->team.slots > 0) team_free(h);
+        return search_alloc(h, nq);
+    }
+    const int k = split_wide_count(h, nq);
+    if (k == 0) {
+        if (h->search.slots > 1) search_free(h);
+        return team_alloc(h, nq);
+    }
+    if (h->search.slots > 2 * k) search_free(h);
+    const int rc = search_alloc(h, k);
+    return rc != NSFS_OK ? rc : team_alloc(h, nq - k);
+}
+
+static int launch_split(nsfs_planner* h, int k_wide, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,
+                        double* d_g_goal, int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_s5) {
+    int rc;
+    if (!h->stream2) {
+        NSFS_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        NSFS_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        NSFS_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    if ((rc = alloc_for_search(h, true, nq)) != NSFS_OK) return rc;
+    nsfs::TeamWork& t = h->team;
+    if (t.order_cap < nq) {
+        cudaFree(t.order); t.order = nullptr; t.order_cap = 0;
+        NSFS_CUDA_TRY(h, cudaMalloc(&t.order, (size_t)nq * sizeof(int32_t)));
+        t.order_cap = nq;
+    }
+    nsfs::launch_start_order(h, d_q, nq, algo == NSFS_ASTAR, t.order);
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    NSFS_CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    // two wide blocks (33 KB each) and up to seven team blocks (17 KB) per SM.  Blocks of two kernels share an SM only under ONE
+    // shared-memory configuration, and the driver raises a kernel's preference to what its own full occupancy needs (228 KB for
+    // the wide kernel): both ask for the maximum
+    h->carveout = 100;
+    rc = nsfs::launch_search(h, 0, algo, mode, k_wide, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5,
+                             t.order, h->stream2, true);
+    if (rc == NSFS_OK)
+        rc = nsfs::launch_search_team(h, algo, mode, nq - k_wide, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5,
+                                      t.order + k_wide, h->stream, true);
+    h->carveout = 0;
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev_join, h->stream2));
+    NSFS_CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    return rc;
+}
+
 static int launch_any_search(nsfs_planner* h, bool team, int kind, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,
                              double* d_g_goal, int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_s5) {
     if (team) {
-        if (h->search.slots > 1) search_free(h);          // the two kernels' per-query state competes for the same HBM
+        const int k_wide = split_wide_count(h, nq);
+        if (k_wide > 0) return launch_split(h, k_wide, algo, mode, nq, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5);
+        const int rc = alloc_for_search(h, true, nq);
+        if (rc != NSFS_OK) return rc;
         return launch_search_team(h, algo, mode, nq, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5);
     }
-    if (nq > 1 && h->team.slots > 0) team_free(h);
+    const int rc = alloc_for_search(h, false, nq);
+    if (rc != NSFS_OK) return rc;
     return launch_search(h, kind, algo, mode, nq, d_q, d_status, d_g_goal, d_path_len, d_settled, d_paths, path_cap, d_s5);
 }
 
@@ -330,8 +406,7 @@ static int run_search_host(nsfs_planner* h, int kind, int algo, int mode, int nq
     const bool team = use_team_kernel(h, kind, algo, nq);
     // find_better_point runs with its state in shared memory unless the wide kernel is forced (the re-run path below)
     const bool small_fb = kind == 1 && h->opt_search_kernel != 1 && h->W >= 3;
-    if (!team && !small_fb && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
-    if (team && (rc = team_alloc(h, nq)) != NSFS_OK) return rc;
+    if (!small_fb && (rc = alloc_for_search(h, team, nq)) != NSFS_OK) return rc;      // outside the timed region
     Timer tm(h);
     if (small_fb)
         rc = launch_fallback_small(h, nq, (const int32_t*)(d + o_q), (int32_t*)(d + o_status), (long long*)(d + o_set),
@@ -476,8 +551,7 @@ int nsfs_plan_batch_device(nsfs_t* h, int algo, int cost_mode, int nq, const int
     if (!nq) return NSFS_OK;
     const long long launches0 = h->launches;
     const bool team = use_team_kernel(h, 0, algo, nq);
-    if (!team && (rc = search_alloc(h, nq)) != NSFS_OK) return rc;
-    if (team && (rc = team_alloc(h, nq)) != NSFS_OK) return rc;
+    if ((rc = alloc_for_search(h, team, nq)) != NSFS_OK) return rc;      // outside the timed region
     if ((rc = ensure_scratch(h, 256)) != NSFS_OK) return rc;
     long long* d_s5 = (long long*)h->d_scratch;
     NSFS_CUDA_TRY(h, cudaMemsetAsync(d_s5, 0, 5 * 8, h->stream));
@@ -845,6 +919,7 @@ int nsfs_set_option(nsfs_t* h, const char* key, long long value) {
     if (!strcmp(key, "team_cell_bytes")) { h->opt_team_cell_bytes = value; team_free(h); return NSFS_OK; }
     if (!strcmp(key, "search_kernel")) { h->opt_search_kernel = value; return NSFS_OK; }
     if (!strcmp(key, "search_order")) { h->opt_search_order = value; return NSFS_OK; }
+    if (!strcmp(key, "split_wide")) { h->opt_split_wide = value; return NSFS_OK; }
     if (!strcmp(key, "graph")) {                            // 0 reference quirk graph, 1 textbook 8-connected grid: rebuild the edge masks
         if (value != 0 && value != 1) return NSFS_E_ARG;
         if (h->opt_graph == value) return NSFS_OK;

@@ -136,6 +136,9 @@ struct nsfs_planner {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // whole call
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // dominant kernel of the call
+    cudaStream_t stream2 = nullptr;                // second stream of a split batch (wide kernel beside the team kernel); made on first use
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int carveout = 0;                              // shared-memory carveout (percent) both search kernels ask for while a split batch runs; 0 = each its own
     int lo_thresh = 0;
     bool have_map = false;
     bool have_raw = false;          // d_infl / d_lo hold the int32 planes of the current map
@@ -164,6 +167,7 @@ struct nsfs_planner {
     long long opt_team_entry_bytes = 0; // batch kernel: 0 = 4-byte open-list entries where cost mode "f" and N <= 2^20 allow, 8 = always 8-byte
     long long opt_team_cell_bytes = 0;  // batch kernel: 0 = by map size (4 up to 2048 cells a side), 4 | 8
     long long opt_team_heap_cap = 0;    // batch kernel: 0 = auto (max(N / 8, 4096) entries; overflow falls back to the wide kernel)
+    long long opt_split_wide = 0;       // batches on the team kernel: k > 0 = the k longest expected queries run one per warp beside it (capi.cu: launch_split); 0 = off
     long long opt_search_order = 0;     // batches larger than the slots: 0 / 1 = start the longest expected queries first, 2 = input order
     long long opt_search_kernel = 0;    // 0 = auto (batches of Astar / Djikstra on the team kernel), 1 = always one query per warp, 2 = team kernel even for one query
     long long opt_field_inner = 0;      // 0 = default (16)
@@ -208,16 +212,20 @@ int launch_field_path(nsfs_planner* h, int gi, int gj, int32_t* d_path, int cap,
 int search_alloc(nsfs_planner* h, int want_slots);
 void search_free(nsfs_planner* h);
 // kind: 0 plan (algo/mode), 1 find_better_point.  All pointers are device pointers; paths optional.
+// A split batch (capi.cu: launch_split) passes its own start order (nq = entries of ext_order, d_q = the whole batch), the stream
+// to launch on, and part = true: no order of its own, no ev2 / ev3 records.
 int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* d_q,
                   int32_t* d_status, double* d_g_goal, int32_t* d_path_len, long long* d_settled,
-                  int32_t* d_paths, int path_cap, long long* d_stats5);
+                  int32_t* d_paths, int path_cap, long long* d_stats5,
+                  const int32_t* ext_order = nullptr, cudaStream_t ext_stream = nullptr, bool part = false);
 
 int team_alloc(nsfs_planner* h, int want_slots);
 void team_free(nsfs_planner* h);
 // order[k] = the k-th query to start, longest expected first (search_team.cu: team_order_kernel); both batch launchers use it
 void launch_start_order(nsfs_planner* h, const int32_t* d_q, int nq, bool heuristic, int32_t* d_order);
 int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status, double* d_g_goal,
-                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5);
+                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5,
+                       const int32_t* ext_order = nullptr, cudaStream_t ext_stream = nullptr, bool part = false);
 
 int launch_inflate(nsfs_planner* h, const int32_t* d_lo, int occ_thresh, double inflation_radius, double cell_size, int32_t* d_infl,
                    uint32_t* d_occ_scratch, int* d_flags);

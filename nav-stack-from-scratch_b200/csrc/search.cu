@@ -662,8 +662,9 @@ int launch_fallback_small(nsfs_planner* h, int nq, const int32_t* d_q, int32_t* 
 
 int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status,
                   double* d_g_goal, int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap,
-                  long long* d_stats5) {
+                  long long* d_stats5, const int32_t* ext_order, cudaStream_t ext_stream, bool part) {
     if (nq <= 0) return NSFS_OK;
+    cudaStream_t stream = ext_stream ? ext_stream : h->stream;
     int rc = search_alloc(h, nq);
     if (rc != NSFS_OK) return rc;
     SearchWork& s = h->search;
@@ -675,8 +676,8 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;     // unknown => fg (grid_planner_core.cpp:274-281)
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
     p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;
-    p.order = nullptr;
-    if (kind != 1 && nq > p.slots && h->opt_search_order != 2) {     // more queries than slots: start the long ones first
+    p.order = ext_order;
+    if (!part && kind != 1 && nq > p.slots && h->opt_search_order != 2) {     // more queries than slots: start the long ones first
         if (s.order_cap < nq) {
             cudaFree(s.order); s.order = nullptr; s.order_cap = 0;
             NSFS_CUDA_TRY(h, cudaMalloc(&s.order, (size_t)nq * sizeof(int32_t)));
@@ -685,20 +686,21 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
         launch_start_order(h, d_q, nq, algo != NSFS_DJIKSTRA, s.order);
         p.order = s.order;
     }
-    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), stream));
     const int block = SEARCH_WARPS_PER_BLOCK * 32;
     const int grid = (p.slots + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK;
     if (kind != 1 && algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA && algo != NSFS_THETASTAR) return NSFS_E_ARG;
-    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+    if (!part) NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, stream));
+    const int carve = h->carveout > 0 ? h->carveout : (int)cudaSharedmemCarveoutMaxShared;
     // 32 KB of shared memory per block (the open lists' top levels): ask for the carveout that keeps six blocks resident
-#define NSFS_WIDE_LAUNCH(A) do { cudaFuncSetAttribute(search_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-                                 search_kernel<A><<<grid, block, 0, h->stream>>>(p); } while (0)
+#define NSFS_WIDE_LAUNCH(A) do { cudaFuncSetAttribute(search_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+                                 search_kernel<A><<<grid, block, 0, stream>>>(p); } while (0)
     if (kind == 1) { p.mode = NSFS_MODE_G; NSFS_WIDE_LAUNCH(kAlgoFallback); }
     else if (algo == NSFS_ASTAR) NSFS_WIDE_LAUNCH(NSFS_ASTAR);
     else if (algo == NSFS_DJIKSTRA) NSFS_WIDE_LAUNCH(NSFS_DJIKSTRA);
     else NSFS_WIDE_LAUNCH(NSFS_THETASTAR);
 #undef NSFS_WIDE_LAUNCH
-    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    if (!part) NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;

@@ -547,8 +547,10 @@ void team_free(nsfs_planner* h) {
 }
 
 int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_t* d_q, int32_t* d_status, double* d_g_goal,
-                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5) {
+                       int32_t* d_path_len, long long* d_settled, int32_t* d_paths, int path_cap, long long* d_stats5,
+                       const int32_t* ext_order, cudaStream_t ext_stream, bool part) {
     if (nq <= 0) return NSFS_OK;
+    cudaStream_t stream = ext_stream ? ext_stream : h->stream;
     int rc = team_alloc(h, nq);
     if (rc != NSFS_OK) return rc;
     TeamWork& s = h->team;
@@ -560,8 +562,8 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
     p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;
-    p.order = nullptr;
-    if (nq > p.slots && h->opt_search_order != 2) {                  // more queries than slots: start the long ones first
+    p.order = ext_order;
+    if (!part && nq > p.slots && h->opt_search_order != 2) {         // more queries than slots: start the long ones first
         if (s.order_cap < nq) {
             cudaFree(s.order); s.order = nullptr; s.order_cap = 0;
             NSFS_CUDA_TRY(h, cudaMalloc(&s.order, (size_t)nq * sizeof(int32_t)));
@@ -570,7 +572,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
         launch_start_order(h, d_q, nq, algo == NSFS_ASTAR, s.order);
         p.order = s.order;
     }
-    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), h->stream));
+    NSFS_CUDA_TRY(h, cudaMemsetAsync(s.work_counter, 0, sizeof(int), stream));
     const int block = TEAM_WARPS_PER_BLOCK * 32;
     const int per_block = TEAM_WARPS_PER_BLOCK * 4;
     const int grid = (p.slots + per_block - 1) / per_block;
@@ -584,10 +586,11 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
         p.div_s = sh;
     }
     if (algo != NSFS_ASTAR && algo != NSFS_DJIKSTRA) return NSFS_E_ARG;
-    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
-    // 16 KB of shared memory per block (the open lists' top levels) x 7 resident blocks: ask for a carveout that holds them
-#define NSFS_TEAM_LAUNCH2(A, M, C, B) do { cudaFuncSetAttribute(search_team_kernel<A, M, C, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 70); \
-                                          search_team_kernel<A, M, C, B><<<grid, block, 0, h->stream>>>(p); } while (0)
+    if (!part) NSFS_CUDA_TRY(h, cudaEventRecord(h->ev2, stream));
+    // 16 KB of shared memory per block (the open lists' top levels) x 9 resident blocks: ask for a carveout that holds them
+    const int carve = h->carveout > 0 ? h->carveout : 70;
+#define NSFS_TEAM_LAUNCH2(A, M, C, B) do { cudaFuncSetAttribute(search_team_kernel<A, M, C, B>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+                                          search_team_kernel<A, M, C, B><<<grid, block, 0, stream>>>(p); } while (0)
 #define NSFS_TEAM_LAUNCH1(A, M, B) do { if (s.cell_bytes == 4) NSFS_TEAM_LAUNCH2(A, M, 4, B); else NSFS_TEAM_LAUNCH2(A, M, 8, B); } while (0)
 #define NSFS_TEAM_LAUNCH(A, M) NSFS_TEAM_LAUNCH1(A, M, 8)
     const bool small_entries = team_entry_bytes(h, p.mode) == 4;
@@ -606,7 +609,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
 #undef NSFS_TEAM_LAUNCH
 #undef NSFS_TEAM_LAUNCH1
 #undef NSFS_TEAM_LAUNCH2
-    NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+    if (!part) NSFS_CUDA_TRY(h, cudaEventRecord(h->ev3, stream));
     h->launches++;
     NSFS_CUDA_TRY(h, cudaGetLastError());
     return NSFS_OK;

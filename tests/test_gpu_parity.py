@@ -179,6 +179,16 @@ def test_batch_kernel_agrees_with_wide_kernel(gpu_lib, spec):
     assert np.array_equal(team["status"], wide["status"]) and np.array_equal(team["settled"], wide["settled"])
     assert np.array_equal(team["path_len"], wide["path_len"]) and np.array_equal(team["paths"], wide["paths"])
     assert same_cost(team["g_goal"], wide["g_goal"])
+    # option "split_wide": the k longest expected queries run one per warp on a second stream beside the team kernel
+    for k_wide in (24, 7):
+        P.set_option("split_wide", k_wide)
+        split = P.plan_batch(algo, mode, qs, path_cap=2048)
+        assert split["stats"]["launches"] == 3                               # start order, wide kernel, team kernel
+        assert split["stats"]["pops"] == wide["stats"]["pops"] and split["stats"]["pushes"] == wide["stats"]["pushes"]
+        assert np.array_equal(split["status"], wide["status"]) and np.array_equal(split["settled"], wide["settled"])
+        assert np.array_equal(split["path_len"], wide["path_len"]) and np.array_equal(split["paths"], wide["paths"])
+        assert same_cost(split["g_goal"], wide["g_goal"])
+    P.set_option("split_wide", 0)
     # a tiny open-list slot: the batch kernel hands those queries to the wide kernel and the results do not change
     P.set_option("team_heap_cap", 64)
     small = P.plan_batch(algo, mode, qs, path_cap=2048)
