@@ -219,7 +219,7 @@ int launch_search(nsfs_planner* h, int kind, int algo, int mode, int nq, const i
                   int32_t* d_paths, int path_cap, long long* d_stats5,
                   const int32_t* ext_order = nullptr, cudaStream_t ext_stream = nullptr, bool part = false);
 
-int team_alloc(nsfs_planner* h, int want_slots);
+int team_alloc(nsfs_planner* h, int nq);        // slots for a batch of nq (search_team.cu: team_slots_wanted)
 void team_free(nsfs_planner* h);
 // order[k] = the k-th query to start, longest expected first (search_team.cu: team_order_kernel); both batch launchers use it
 void launch_start_order(nsfs_planner* h, const int32_t* d_q, int nq, bool heuristic, int32_t* d_order);

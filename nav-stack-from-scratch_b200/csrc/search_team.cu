@@ -502,7 +502,17 @@ static int team_entry_bytes(const nsfs_planner* h, int mode) {
     return (mode == NSFS_MODE_F && h->N <= (1ll << 20)) ? 4 : 8;
 }
 
-int team_alloc(nsfs_planner* h, int want_slots) {
+// Teams in flight for a batch of nq.  More teams in flight raise the throughput (C4, 65 536 queries: 5 820 queries/s on 16 576
+// slots, 6 276 on 21 312) but every query then runs slower, and a launch lasts as long as its slowest query: a batch that fits the
+// slots less than twice over finishes soonest with HALF of it in flight (32 768 queries: 6.5 s on 16 384 slots, 7.0 s on 12 288,
+// 7.9 s on 21 312; 16 384 queries: 5.4 s on 8 192 slots, 5.6 s on 12 288, 6.1 s on 16 384; profiles/r02_search.md).
+static long long team_slots_wanted(const nsfs_planner* h, int nq, long long cap) {
+    long long want = nq < 1 ? 1 : nq;
+    if (h->opt_max_slots <= 0 && nq > 64) want = (((long long)nq + 1) / 2 + 15) & ~15ll;      // whole blocks of 16 teams
+    return want < cap ? want : cap;
+}
+
+int team_alloc(nsfs_planner* h, int nq) {
     TeamWork& s = h->team;
     const int cb = team_cell_bytes(h);
     // open-list slot: N / 8 entries with 8-byte records (round 1), N / 32 with 4-byte records, where the point is the footprint
@@ -510,11 +520,10 @@ int team_alloc(nsfs_planner* h, int want_slots) {
     const long long auto_cap = cb == 4 ? h->N / 32 : h->N / 8;
     long long heap_cap = h->opt_team_heap_cap > 0 ? h->opt_team_heap_cap : (auto_cap > 4096 ? auto_cap : 4096);
     if (heap_cap > (1ll << 31) - 64) heap_cap = (1ll << 31) - 64;
-    if (want_slots < 1) want_slots = 1;
     // warps of slots per SM: 28 with 8-byte records (what 0.85 of a B200's HBM holds at 1024^2, 9 MB per slot), 36 with 4-byte
     // records (the register file's limit at 55 registers per thread; 4.25 MB per slot)
     const long long cap = h->opt_max_slots > 0 ? h->opt_max_slots * 4 : (long long)h->sm_count * (cb == 4 ? 36 : 28) * 4;
-    long long slots = want_slots < cap ? want_slots : cap;
+    long long slots = team_slots_wanted(h, nq, cap);
     // reuse: enough slots, or an allocation made for at least this many that free HBM clamped (see search_alloc)
     if (s.cells && s.cell_bytes == cb && s.heap_cap >= heap_cap && (s.slots >= slots || s.target >= slots)) return NSFS_OK;
     team_free(h);
@@ -558,7 +567,7 @@ int launch_search_team(nsfs_planner* h, int algo, int mode, int nq, const int32_
     p.out_mask = h->d_out_mask; p.cells = s.cells; p.heap = s.heap; p.epoch = s.epoch; p.work_counter = s.work_counter;
     p.H = h->H; p.W = h->W; p.N = h->N; p.heap_cap = s.heap_cap; p.heap_stride = (s.heap_cap + 5) & ~1ll;
     p.cell_stride = (long long)((((size_t)h->N * s.cell_bytes + 15) / 16) * 16);
-    p.slots = nq < s.slots ? nq : s.slots;
+    p.slots = (int)team_slots_wanted(h, nq, s.slots);
     p.mode = (mode == NSFS_MODE_F || mode == NSFS_MODE_G) ? mode : NSFS_MODE_FG;
     p.nq = nq; p.q = d_q; p.status = d_status; p.g_goal = d_g_goal; p.path_len = d_path_len; p.settled = d_settled;
     p.paths = d_paths; p.path_cap = path_cap; p.stats5 = d_stats5;

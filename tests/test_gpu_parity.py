@@ -286,7 +286,7 @@ def test_batch_larger_than_the_slots_and_its_start_order(gpu_lib, oracle_mod, al
     P = gpu_lib.Planner(96, 128)
     P.set_map(infl, lo)
     P.set_option("search_kernel", 2)
-    free = P.plan_batch(algo, mode, qs, path_cap=700)                         # 150 slots: everything in flight at once
+    free = P.plan_batch(algo, mode, qs, path_cap=700)                         # 80 slots (half the batch in flight: team_slots_wanted)
     P.set_option("max_slots", 2)                                              # 2 warps = 8 slots: 19 waves
     ordered = P.plan_batch(algo, mode, qs, path_cap=700)
     P.set_option("search_order", 2)                                           # the same waves in input order
