@@ -260,7 +260,7 @@ void*       nsfs_stream(nsfs_t* h);                  /* cudaStream_t of the hand
  *   "team_cell_bytes"  4 | 8: per-cell record of the batch kernel (0 = 4 up to 2048 cells a side);  "team_entry_bytes"  8 = always
  *                    8-byte open-list entries (0 = 4-byte ones where cost mode "f" and at most 2^20 cells allow)
  *   "split_wide"     k > 0: the k longest expected queries of a batch run one per warp on a second stream beside the batch
- *                    kernel (measured slower - the two kernels do not overlap - so off by default)
+ *                    kernel (measured slower than the unsplit batch, so off by default)
  *   "active_row_lo/hi", "count_row_lo/hi"      row windows of a shard (see the row-partitioned field above)
  * Environment overrides read by nsfs_create (experiments / running the test-suite per solver): NSFS_FIELD_MODE, NSFS_FIELD_FENCE,
  * NSFS_SEARCH_ORDER, NSFS_MAX_SLOTS, NSFS_SPLIT_WIDE, NSFS_FIELD_GATE. */

@@ -304,10 +304,11 @@ static bool use_team_kernel(const nsfs_planner* h, int kind, int algo, int nq) {
 // queries (900 000 expansions) take several seconds on an 8-lane team under full load while a 32-lane warp walks the same chain
 // about twice as fast; so the head of the start order (the k longest expected queries, team_order_kernel) can go to the wide kernel
 // on a second stream while the team kernel takes the rest.  Statuses, paths and settled counts do not depend on which kernel ran a
-// query (costs agree to the last few ulps: fp64 sums there, a + b * sqrt(2) here).  MEASURED: on this driver the two kernels do not
-// overlap - 16 384 C4 queries take 8.2 s split against 6.1 s on the team kernel alone, the same with 592, 1 184 or 2 368 wide
-// queries and with either carveout (profiles/r02_search.md) - so nothing selects it; it stays as a tested option for whoever
-// finds what serialises them.
+// query (costs agree to the last few ulps: fp64 sums there, a + b * sqrt(2) here).  MEASURED (profiles/r02_search.md section 4): the
+// first split launch of a process serialises (the second kernel's module is loaded lazily, which waits for the first); from the
+// second launch on the kernels overlap, and the batch is STILL slower than unsplit - 16 384 C4 queries 5.8 - 6.0 s against 5.4 s,
+// 65 536 queries 12.1 s against 10.4 s: next to the team kernel's load the wide kernel's long queries run no faster than they
+// would on a team.  So nothing selects it; it stays as a tested option.
 static int split_wide_count(const nsfs_planner* h, int nq) {
     if (h->opt_split_wide <= 0 || h->opt_search_order == 2) return 0;
     long long k = h->opt_split_wide;
