@@ -197,6 +197,42 @@ def test_batch_kernel_agrees_with_wide_kernel(gpu_lib, spec):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["f", "fg"])
+def test_far_goals_and_record_sizes_on_the_batch_kernel(gpu_lib, oracle_mod, mode):
+    """The batch kernel's open-list entries hold (int)f in 12 bits (4-byte entries) or 16 (8-byte), the wide kernel's in 18, the
+    reference compares full ints.  A query whose keys outgrow its entry is handed on (NSFS_E_HEAP inside, replayed on the wide
+    kernel) and returns what the reference returns; only beyond 2^18 is NSFS_E_HEAP the answer (nsfs.h).  The record / entry size
+    options change nothing."""
+    infl, lo = mapgen.synth_map(96, 128, 0.10, 88)
+    qs = mapgen.sample_queries(infl, lo, 80, 88)
+    far = {7: (5000, 3), 8: (70000, 10), 9: (40, 4500), 10: (-3000, 5)}       # goals off the grid: never reached, the whole component is settled
+    for t, g in far.items():
+        qs[t, 2:] = g
+    qs[11, 2:] = (300000, 3)                                                  # (int)f >= 2^18
+    ok = np.arange(80) != 11
+    P = gpu_lib.Planner(96, 128)
+    P.set_map(infl, lo)
+    P.set_option("search_kernel", 1)
+    wide = P.plan_batch("astar", mode, qs, path_cap=700)
+    assert wide["status"][11] == gpu_lib.E_HEAP and (wide["status"][ok] == 0).all()
+    O = oracle_mod.Oracle(infl, lo)
+    for t in list(far) + [0, 1, 50]:
+        o = O.plan(oracle_mod.ASTAR, mode, qs[t, :2], qs[t, 2:])
+        n = len(o["path"])
+        assert wide["path_len"][t] == n and np.array_equal(wide["paths"][t][:n], o["path"]), t
+        assert wide["settled"][t] == o["settled"] and same_cost(wide["g_goal"][t], o["g_goal"]), t
+    P.set_option("search_kernel", 2)
+    for cell_bytes, entry_bytes in ((0, 0), (8, 0), (0, 8), (8, 8)):
+        P.set_option("team_cell_bytes", cell_bytes)
+        P.set_option("team_entry_bytes", entry_bytes)
+        team = P.plan_batch("astar", mode, qs, path_cap=700)
+        assert np.array_equal(team["status"], wide["status"]), (cell_bytes, entry_bytes)
+        assert np.array_equal(team["settled"][ok], wide["settled"][ok]) and np.array_equal(team["path_len"][ok], wide["path_len"][ok])
+        assert np.array_equal(team["paths"][ok], wide["paths"][ok]) and same_cost(team["g_goal"][ok], wide["g_goal"][ok])
+    P.close()
+
+
+@pytest.mark.gpu
 def test_fallback_in_shared_memory_agrees_with_the_wide_kernel(gpu_lib, oracle_mod):
     """find_better_point normally runs with its whole state in shared memory (256-slot table, search.cu
     fallback_small_kernel); searches that outgrow it are re-run on the wide kernel.  Same cells either way, and the
