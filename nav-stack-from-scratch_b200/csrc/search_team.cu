@@ -7,14 +7,16 @@
 // Eight lanes are also exactly the 8 neighbours of an expansion.
 //
 // What is replayed is unchanged (see search.cu): libstdc++'s push_heap / pop_heap with the reference's three comparators,
-// int-truncated keys, pushes in NB_LUT order, closed cells re-labelled.  Entries here are 64-bit words
+// int-truncated keys, pushes in NB_LUT order, closed cells re-labelled.  Entries are 64-bit words
 //   high word  (int)f : 16 | (int)g : 16        low word  flat key (29 bits)
-// so a comparator is ONE 32-bit compare on the high word (f: hi >> 16, g: hi & 0xffff, fg: hi), chosen at compile time
-// (the cost mode is a template parameter).  An f or g beyond 16 bits ends the query with NSFS_E_HEAP like a step-count
-// overflow (re-run on the wide kernel, whose entries hold f:18 | g:17).
-// The top seven levels of every open list (positions 1..127, 1 KB per team) live in SHARED memory: a sift-down starts with
-// two 3-level chunks at shared-memory latency, the root is read without a trip to L2 / HBM, and a push that rises into the
-// top meets it there (ncu round 1: ~8 dependent global round trips per pop, long_scoreboard the first stall).
+// or, where the comparator is "f" and a key fits 20 bits, 32-bit words (int)f : 12 | key : 20 (EntryT below).  Either way a
+// comparator is ONE 32-bit compare (f: hi >> 16, g: hi & 0xffff, fg: hi; e >> 20), chosen at compile time (cost mode and entry
+// size are template parameters).  An f or g beyond its bits ends the query with NSFS_E_HEAP like a step-count overflow (re-run on
+// the wide kernel, whose entries hold f:18 | g:17).
+// The first 1 KB of every open list (positions 1..127 of 8-byte entries = seven levels, 1..255 of 4-byte ones = eight) lives in
+// SHARED memory: a sift-down starts with two 3-level chunks at shared-memory latency, the root is read without a trip to
+// L2 / HBM, and a push that rises into the top meets it there (ncu round 1: ~8 dependent global round trips per pop,
+// long_scoreboard the first stall).
 //   pop   3-level chunks: team lane t < 7 owns internal node t of the subtree under the hole and loads both children
 //         with one 128-bit load; two ballots give the path through the three levels; stop at the first picked child that
 //         sorts after the displaced element (same final array as sink-to-leaf + sift-up, priorities are monotone on a path)
