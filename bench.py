@@ -722,6 +722,8 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
 
     peak, peak_src = peaks()
     value = total * args.steps / (dev_ms_max * 1e-3)
+    # capi.cu use_team_kernel: a rank's share of up to 2 x SMs x 32 queries (9 472) runs one query per warp (no ncu traffic capture of that one)
+    main_kernel = "search_team_kernel" if nq > 2 * torch.cuda.get_device_properties(dev).multi_processor_count * 32 else "search_kernel"
     alg_bytes = BYTES_PER_SETTLED * settled_all / (args.steps * world)          # per launch of the dominant kernel (one per rank and step)
     achieved = alg_bytes / (main_ms_max / args.steps * 1e-3) / 1e9
     line = {
@@ -730,7 +732,7 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": shared_config("c4"),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic("search_team_kernel", nq), "kernel": "search_team_kernel", "peak_source": peak_src,
+                     "traffic": ncu_traffic(main_kernel, nq), "kernel": main_kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": main_ms_max / args.steps,
                      "note": "per GPU: 9.125 B x the reference-settled cells of that rank's queries over its kernel time (max over ranks)"},
         "e2e": {"value": total * e2e_steps / e2e_sec, "unit": "queries/s",
@@ -739,6 +741,7 @@ def ours_c4(args, torch, dist, rank, world, local, dev):
                 "path": f"{what}: " + ("GpuAstar::planBatch" if world == 1 else "GpuAstar::planBatchSharded over nsfs_host::DeviceGroup (map broadcast + "
                         "result all-gather over NCCL, called from C++)") + " on a MapData whose std::vector<int> planes are uploaded on every call (page-locked once by the child: MapSync::EveryCallPinned, its default), "
                         "queries from host memory, per-query results back to the host",
+                "l2": "not flushed between e2e steps (the resident line flushes it; at 10 s per step the difference is within the noise)",
                 "same_results_as_resident_path": e2e_same},
         "gpu_launches": launches_all,
         "clocks": sampler.finish() if sampler else None,
